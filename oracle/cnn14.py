@@ -1,0 +1,166 @@
+"""Oracle: AFx-Rep encoder, embedding function and fitness (test infrastructure only).
+
+Restates, with plain torch CPU fp32 ops:
+  * ``Cnn14.forward``                         reference st_ito/models/panns.py:209-281
+    (ConvBlock: conv3x3 -> BN(eval) -> ReLU twice, then avg-pool, panns.py:25-80)
+  * ``get_param_embeds``                      reference st_ito/utils.py:444-508
+  * the cosine fitness inside ``evaluate``    reference st_ito/style_transfer.py:544-573
+State-dict keys are the reference's so weights interchange
+with the reference's own ``Cnn14`` -- that is how tests/golden pins this file.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import frontend
+
+CHANNELS = (1, 64, 128, 256, 512, 1024, 2048)
+
+# AFx-Rep hyper-parameters: reference cfg/model/pretext/param-panns-concat-l2.yaml:16-25
+AFX_REP_ARGS = dict(embed_dim=512, sample_rate=48000, window_size=2048, hop_size=1024, mel_bins=128,
+                    fmin=20, fmax=20000, use_batchnorm=True, input_norm="minmax")
+
+
+class _Block(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, 1, 1, bias=False)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.bn2 = nn.BatchNorm2d(cout)
+        for conv in (self.conv1, self.conv2):  # panns.py:10-16
+            nn.init.xavier_uniform_(conv.weight)
+
+    def forward(self, x, pool):
+        x = F.relu(self.bn1(self.conv1(x)))
+        x = F.relu(self.bn2(self.conv2(x)))
+        return F.avg_pool2d(x, kernel_size=pool)
+
+
+class OracleCnn14(nn.Module):
+    """Same parameters / buffers / key names as the reference's ``Cnn14`` (minmax, batchnorm)."""
+
+    def __init__(self, embed_dim=512, sample_rate=48000, window_size=2048, hop_size=1024, mel_bins=128,
+                 fmin=20, fmax=20000, use_batchnorm=True, input_norm="minmax"):
+        super().__init__()
+        assert use_batchnorm and input_norm == "minmax", "oracle covers the AFx-Rep configuration"
+        self.spectrogram_extractor = frontend.Spectrogram(n_fft=window_size, hop_length=hop_size,
+                                                          win_length=window_size)
+        self.logmel_extractor = frontend.LogmelFilterBank(sr=sample_rate, n_fft=window_size, n_mels=mel_bins,
+                                                          fmin=fmin, fmax=fmax, ref=1.0, amin=1e-10, top_db=None)
+        self.bn0 = nn.BatchNorm2d(mel_bins)  # present in checkpoints, unused with minmax (panns.py:178,233)
+        for i in range(6):
+            setattr(self, f"conv_block{i + 1}", _Block(CHANNELS[i], CHANNELS[i + 1]))
+        self.fc_mid = nn.Linear(2048, embed_dim)
+        self.fc_side = nn.Linear(2048, embed_dim)
+        for fc in (self.fc_mid, self.fc_side):
+            nn.init.xavier_uniform_(fc.weight)
+            fc.bias.data.zero_()
+
+    def logmel(self, x):
+        """x [bs, chs, L] -> normalised log-mel [bs*chs, 1, T, mel] in the row order of panns.py:227."""
+        bs, chs, L = x.shape
+        if chs == 2:
+            mid = (x[:, 0, :] + x[:, 1, :]) / 2
+            side = (x[:, 0, :] - x[:, 1, :]) / 2
+            x = torch.stack([mid, side], dim=1)
+        elif chs != 1:
+            raise ValueError(f"Invalid number of channels: {chs}")
+        x = x.reshape(bs * chs, L)
+        return frontend.minmax_norm(self.logmel_extractor(self.spectrogram_extractor(x)))
+
+    def body(self, feats, bs, chs):
+        x = feats
+        for i in range(6):
+            x = getattr(self, f"conv_block{i + 1}")(x, (2, 2) if i < 5 else (1, 1))
+        x = x.mean(dim=3)
+        x = x.max(dim=2).values + x.mean(dim=2)
+        x = x.view(bs, chs, -1)
+        mid = self.fc_mid(x[:, 0, :])
+        side = self.fc_side(x[:, 1, :]) if chs == 2 else mid
+        return mid, side
+
+    def forward(self, x):
+        bs, chs, _ = x.shape
+        return self.body(self.logmel(x), bs, chs)
+
+
+def make_encoder(seed: int = 0, bn_stats: bool = True, centre_heads: bool = False) -> OracleCnn14:
+    """Seeded synthetic AFx-Rep weights (no checkpoint is obtainable offline).
+
+    Convs/linears use the reference's Xavier-uniform init; with ``bn_stats`` the
+    BatchNorm layers get non-trivial seeded gamma/beta/running stats so that BN
+    folding in the CUDA path is actually exercised.
+    """
+    g = torch.Generator().manual_seed(seed)
+    prev = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    try:
+        m = OracleCnn14(**AFX_REP_ARGS)
+    finally:
+        torch.random.set_rng_state(prev)
+    if bn_stats:
+        for mod in m.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                n = mod.num_features
+                mod.weight.data = 0.6 + 0.8 * torch.rand(n, generator=g)
+                mod.bias.data = 0.2 * torch.randn(n, generator=g)
+                mod.running_mean.data = 0.1 * torch.randn(n, generator=g)
+                mod.running_var.data = 0.5 + torch.rand(n, generator=g)
+    m.eval()
+    return m
+
+
+def get_param_embeds(x: torch.Tensor, model: nn.Module, sample_rate: float) -> dict:
+    """utils.py:444-508 for sample_rate == 48000, requires_grad False, dropout 0."""
+    assert sample_rate == 48000, "the oracle does not restate torchaudio.functional.resample"
+    x = x.type_as(next(model.parameters()))
+    for b in range(x.shape[0]):  # in-place, per item over all channels jointly (utils.py:473-474)
+        x[b, ...] /= x[b, ...].abs().max().clamp(1e-8)
+    with torch.no_grad():
+        mid, side = model(x)
+    if torch.isnan(mid).any():
+        mid = torch.nan_to_num(mid)
+    elif torch.isnan(side).any():
+        side = torch.nan_to_num(side)
+    return {"mid": F.normalize(mid, p=2, dim=-1), "side": F.normalize(side, p=2, dim=-1)}
+
+
+def fitness(output_embeds: dict, target_embeds: dict) -> torch.Tensor:
+    """style_transfer.py:544-571: mean over keys of -cosine_similarity(out[P,E], tgt[1,E])."""
+    dists = [-torch.cosine_similarity(output_embeds[k], target_embeds[k], dim=-1) for k in output_embeds]
+    return torch.stack(dists, dim=0).mean(dim=0)
+
+
+def evaluate(W, x: torch.Tensor, sample_rate, plugins, model, target_embeds):
+    """style_transfer.py:474-573, serial branch, random_crop=False.  x is [1, chs, L]."""
+    import numpy as np
+
+    from oracle import dsp
+
+    L = x.shape[-1]
+    if L <= 262144:  # style_transfer.py:505-518
+        x = F.pad(x, (0, 262144 - L))
+    audios = [torch.from_numpy(dsp.process_audio(x.squeeze(0).numpy(), np.asarray(w), sample_rate, plugins))
+              for w in W]
+    audios = torch.stack(audios, dim=0)
+    embeds = get_param_embeds(audios, model, sample_rate)
+    return fitness(embeds, target_embeds).tolist(), embeds, audios
+
+
+def flops_per_signal(T: int, mel: int = 128) -> int:
+    """2 * MACs of the 12 convs for one T x mel log-mel image."""
+    h, w, total = T, mel, 0
+    for i in range(6):
+        cin, cout = CHANNELS[i], CHANNELS[i + 1]
+        total += h * w * cout * 9 * cin + h * w * cout * 9 * cout
+        if i < 5:
+            h, w = h // 2, w // 2
+    return 2 * total
+
+
+assert math.isclose(flops_per_signal(469) / 1e9, 37.2, rel_tol=0.01)
