@@ -1,0 +1,167 @@
+/*
+ * stito.h -- C ABI of libstito.so, the B200 (sm_100a) implementation of st-ito's
+ * CMA-ES population evaluation path.
+ *
+ * Every entry point replaces a piece of the reference's Python path (citations are
+ * file:line in csteinmetz1/st-ito); the reference-side binding is a ctypes stub,
+ * shown in INTEGRATION.md and implemented in st_ito_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no torch / C++ types;
+ *   - every function returns 0 on success or a negative STITO_E* code; the message
+ *     is available from stito_last_error() (thread-local);
+ *   - audio is float32, row-major [chs, L] or [P, chs, L]; parameter vectors are
+ *     float64 on [0,1] exactly as pycma hands them to evaluate();
+ *   - data pointers may be HOST or DEVICE pointers (detected with
+ *     cudaPointerGetAttributes); the library never frees caller memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream);
+ *     calls that write to host memory return after the copy has completed;
+ *   - one handle = one host thread at a time (the reference's plugin objects are
+ *     stateful and not re-entrant either, style_transfer.py:76-92).
+ */
+#ifndef STITO_H
+#define STITO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define STITO_API __attribute__((visibility("default")))
+#else
+#define STITO_API
+#endif
+
+#define STITO_OK 0
+#define STITO_EINVAL (-1)   /* malformed descriptor / argument                       */
+#define STITO_ECUDA (-2)    /* CUDA runtime error (message holds cudaGetErrorString) */
+#define STITO_ESTATE (-3)   /* call order: no input / target / encoder set           */
+#define STITO_ENOMEM (-4)
+
+#define STITO_MAX_FX 8
+#define STITO_MAX_FX_PARAMS 24
+#define STITO_EMBED_DIM_MAX 1024
+
+/* Effects of the reference's built-in ("Basic*") plugin family, st_ito/effects.py:800-959. */
+enum stito_fx_kind {
+    STITO_FX_EQ = 0,         /* BasicParametricEQ  effects.py:800-873 (18 parameters)            */
+    STITO_FX_COMPRESSOR = 1, /* BasicCompressor    effects.py:876-897 (4)                        */
+    STITO_FX_DISTORTION = 2, /* BasicDistortion    effects.py:900-914 (2)                        */
+    STITO_FX_DELAY = 3,      /* BasicDelay         effects.py:917-934 (3)                        */
+    STITO_FX_REVERB = 4      /* BasicReverb        effects.py:937-959 (4)                        */
+};
+
+/* One entry of the reference's ordered `plugins` dict (run_optim.py:376-407,
+ * style_transfer.py:17-42), flattened.  Effect parameters are listed in the order of the
+ * plugin's `.parameters` dict; `our_bypass` slots consume a w index but map to nothing
+ * (style_transfer.py:88-92 never skips the plugin). */
+typedef struct {
+    int32_t kind;                             /* enum stito_fx_kind                                   */
+    int32_t num_channels;                     /* plugins[name]["num_channels"]: 1 or 2                */
+    int32_t num_params;                       /* effect parameters described below (excl. our_bypass) */
+    int32_t w_index[STITO_MAX_FX_PARAMS];     /* index into w, or -1: use fixed_raw                   */
+    double fixed_raw[STITO_MAX_FX_PARAMS];    /* raw_value of fixed_parameters (Parameter.set_value)  */
+} stito_fx_desc;
+
+typedef struct {
+    int32_t num_fx;
+    int32_t num_w;                /* D: length of a parameter vector                          */
+    int32_t normalize_stages;     /* process_audio(normalize_stages=...) style_transfer.py:106 */
+    int32_t reserved;
+    double sample_rate;
+    stito_fx_desc fx[STITO_MAX_FX];
+} stito_chain_desc;
+
+/* AFx-Rep encoder (st_ito/models/panns.py:121-207) weights, HOST pointers, float32, in the
+ * layouts of the reference state_dict.  Index 2*b is conv_block{b+1}.conv1
+ * (+bn1), 2*b+1 is conv2 (+bn2).  The library folds eval-mode BatchNorm into the convolutions. */
+typedef struct {
+    int32_t n_fft, hop, n_mels, embed_dim; /* 2048, 1024, 128, 512                              */
+    float bn_eps;                          /* 1e-5                                               */
+    int32_t reserved;
+    const float *conv_w[12];               /* [Cout, Cin, 3, 3]                                  */
+    const float *bn_weight[12], *bn_bias[12], *bn_mean[12], *bn_var[12]; /* [Cout]               */
+    const float *fc_mid_w, *fc_mid_b;      /* [embed_dim, 2048], [embed_dim]                     */
+    const float *fc_side_w, *fc_side_b;
+    const float *mel_w;                    /* logmel_extractor.melW [n_fft/2+1, n_mels]          */
+} stito_encoder_weights;
+
+typedef struct stito_handle stito_handle;
+
+/* Per-stage device times of the last stito_eval_population call (CUDA events on the launch
+ * stream), the kernels it launched and the algorithmic work it did. */
+typedef struct {
+    float ms_dsp, ms_frontend, ms_encoder, ms_fitness, ms_total;
+    int32_t launches;            /* kernels of this library launched by the call                */
+    int32_t precision;           /* encoder arithmetic used: 0 = fp32 SIMT, 1 = fp16x3 tcgen05  */
+    double encoder_flop;         /* 2*MACs of the 12 convolutions + heads                       */
+    double dsp_bytes, frontend_bytes; /* algorithmic HBM bytes                      */
+    float ms_conv[12];           /* per conv layer                                              */
+} stito_timing;
+
+/* Create an evaluator for (chain, encoder) on CUDA device `device`.  `weights` may be NULL:
+ * the handle then only renders audio (plugin.process / process_audio).
+ * Replaces: load_plugins + model construction, style_transfer.py:17-42, utils.py:511-551. */
+STITO_API int stito_create(const stito_chain_desc *chain, const stito_encoder_weights *weights, int device,
+                 stito_handle **out);
+STITO_API void stito_destroy(stito_handle *h);
+
+/* Swap the effect chain (keeps weights, input and target). */
+STITO_API int stito_set_chain(stito_handle *h, const stito_chain_desc *chain);
+
+/* Encoder arithmetic: 0 = fp32 CUDA cores (bit-for-bit conv semantics of the oracle up to
+ * summation order), 1 = error-compensated fp16x3 on tcgen05 tensor cores (default). */
+STITO_API int stito_set_precision(stito_handle *h, int precision);
+
+/* Upload the input waveform x[chs, L].  The device copy is zero-padded to max(L, min_len) so
+ * that evaluate()'s "pad to 262144" policy (style_transfer.py:518) is a view, not a copy.
+ * Replaces: x = input_audio.clone(), style_transfer.py:623. */
+STITO_API int stito_set_input(stito_handle *h, const float *x, int chs, int64_t L, int64_t min_len);
+
+/* Target embeddings: either computed here from audio (peak-normalise per item, encoder, L2
+ * normalise: embed_func(target_audio), style_transfer.py:456-460) or supplied directly. */
+STITO_API int stito_set_target(stito_handle *h, const float *target, int chs, int64_t L);
+STITO_API int stito_set_target_embeds(stito_handle *h, const float *mid, const float *side, int embed_dim);
+
+/* evaluate(W, x, ...) of style_transfer.py:474-573 for one population:
+ *   for each w: process_audio(x[:, start:start+len], w)  -> peak-normalised audio
+ *   get_param_embeds -> L2-normalised mid/side embeddings -> fitness = mean_k(-cos(out_k, tgt_k)).
+ * W is [P, D] float64 row-major (host or device).  Outputs (each nullable, host or device):
+ *   fitness [P]; embeds [2, P, embed_dim] (mid then side); audio [P, out_chs, len]. */
+STITO_API int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_t start,
+                          int64_t len, float *fitness, float *embeds, float *audio, void *stream);
+
+/* process_audio (style_transfer.py:45-115) for P parameter vectors on an arbitrary signal:
+ * x[chs, L] -> y[P, out_chs, L].  final_normalize=1 applies the closing peak normalisation
+ * (style_transfer.py:113); 0 returns the raw chain output (what plugin.process returns). */
+STITO_API int stito_process(stito_handle *h, const float *x, int chs, int64_t L, const double *W, int P,
+                  int D, int final_normalize, float *y, void *stream);
+
+/* Channels produced by the chain for a chs-channel input (mono is up-mixed by 2-channel plugins,
+ * style_transfer.py:94-95). */
+STITO_API int stito_out_channels(const stito_handle *h, int chs);
+
+/* Cnn14.forward (panns.py:209-281) on x[B, chs, L]; peak_normalize=1 first divides every item by
+ * its peak (utils.py:473-474).  Writes RAW (un-normalised) mid/side embeddings [B, embed_dim]. */
+STITO_API int stito_embed(stito_handle *h, const float *x, int B, int chs, int64_t L, int peak_normalize,
+                float *mid, float *side, void *stream);
+
+/* Normalised log-mel features of x[B, chs, L] (panns.py:219-245): out [B*chs, T, n_mels],
+ * T = L / hop + 1, row order b0-mid, b0-side, b1-mid, ... */
+STITO_API int stito_logmel(stito_handle *h, const float *x, int B, int chs, int64_t L, float *out,
+                 void *stream);
+
+STITO_API int stito_get_timing(const stito_handle *h, stito_timing *out);
+
+/* Thread-local message of the last failing call. */
+STITO_API const char *stito_last_error(void);
+
+/* Library/ABI version: major*10000 + minor*100 + patch. */
+STITO_API int stito_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STITO_H */

@@ -1,0 +1,595 @@
+// DSP kernels of the effect chain (K1): parametric EQ, compressor, distortion, delay, Freeverb,
+// peak tracking.  Replaces the per-candidate CPU loop of the reference's process_audio
+// (st_ito/style_transfer.py:45-115) and the Basic* plugins (st_ito/effects.py:800-959).
+//
+// Parallelisation (candidate x channel x TIME where the recurrence allows it):
+//   EQ          6 cascaded biquads are LTI: the signal is cut into 512-sample chunks, every chunk
+//               is filtered from a zero state in parallel (fp64), the 12-dim chunk-boundary states
+//               are stitched with the 12x12 state-transition matrix, then every chunk is re-run from
+//               its true initial state.  Arithmetic per sample is scipy.signal.lfilter's order.
+//   compressor  the ballistics filter is a data-dependent (non-linear) recurrence: one lane per
+//               stream runs it serially on a 4-op critical path; the gain computer (powf) and all
+//               memory traffic are done by the full warp.
+//   Freeverb    delay lines live in shared memory (one CTA per candidate); comb feedback has a lag
+//               >= 1214 samples and all-pass >= 244, so blocks of 224 samples are time-parallel; the
+//               only lag-1 recurrence (the comb damping one-pole) is a 32-lane affine scan.
+//   delay       lag-d feedback: the d residue classes are independent serial chains.
+// All float arithmetic uses explicit _rn intrinsics where the oracle (compiled with
+// -ffp-contract=off) rounds each operation separately.
+#include "stito_internal.h"
+
+namespace stito {
+
+namespace {
+
+__device__ __forceinline__ float load_in(const SigView &v, int p, int c, int64_t n) {
+    return __ldg(v.base + (int64_t)p * v.stride_p + (int64_t)c * v.stride_c + n);
+}
+
+__device__ __forceinline__ float clip_peak(const float *in_peak, int p) {
+    // np.clip(np.max(np.abs(x)), a_min=1e-8): peaks are stored as float bits (atomicMax on unsigned)
+    return fmaxf(in_peak[p], 1e-8f);
+}
+
+__device__ __forceinline__ void atomic_peak(unsigned *peak, int p, float v) {
+    // v >= 0: IEEE ordering of non-negative floats equals unsigned ordering of their bits
+    if (v > 0.0f) atomicMax(peak + p, __float_as_uint(v));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------ EQ
+// One sample through the cascade, scipy.signal.lfilter evaluation order:
+//   y = z0 + b0*x;  z0 = (z1 + b1*x) - a1*y;  z1 = b2*x - a2*y       cf = {b0,b1,b2,a1,a2}
+__device__ __forceinline__ double eq_step(double v, const double (&cf)[6][5], double (&z0)[6],
+                                          double (&z1)[6]) {
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+        const double y = __dadd_rn(z0[s], __dmul_rn(cf[s][0], v));
+        z0[s] = __dsub_rn(__dadd_rn(z1[s], __dmul_rn(cf[s][1], v)), __dmul_rn(cf[s][3], y));
+        z1[s] = __dsub_rn(__dmul_rn(cf[s][2], v), __dmul_rn(cf[s][4], y));
+        v = y;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void eq_load_coefs(const double *coefs, int p, double (&cf)[6][5]) {
+#pragma unroll
+    for (int s = 0; s < 6; ++s)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) cf[s][k] = __ldg(coefs + ((int64_t)p * 6 + s) * 5 + k);
+}
+
+// APPLY = false: zero-state run, writes the chunk's final 12-state to state[stream][i][k].
+// APPLY = true : starts from state[stream][i][k], writes the filtered chunk and tracks the peak.
+template <bool APPLY>
+__global__ void __launch_bounds__(128) eq_chunk_kernel(SigView in, const float *in_peak, float *out,
+                                                       int chs, int64_t L, int K, const double *coefs,
+                                                       double *state, unsigned *out_peak) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stream = blockIdx.y;
+    const int p = stream / chs, c = stream - p * chs;
+    const bool active = k < K;
+    float pk = 0.0f;
+    if (active) {
+        double cf[6][5], z0[6], z1[6];
+        eq_load_coefs(coefs, p, cf);
+        double *st = state + (int64_t)stream * kEqStates * K + k;
+        if (APPLY) {
+#pragma unroll
+            for (int s = 0; s < 6; ++s) { z0[s] = st[(int64_t)(2 * s) * K]; z1[s] = st[(int64_t)(2 * s + 1) * K]; }
+        } else {
+#pragma unroll
+            for (int s = 0; s < 6; ++s) { z0[s] = 0.0; z1[s] = 0.0; }
+        }
+        const int64_t n0 = (int64_t)k * kEqChunk;
+        const int len = (int)min((int64_t)kEqChunk, L - n0);
+        const float *src = in.base + (int64_t)p * in.stride_p + (int64_t)c * in.stride_c + n0;
+        float *dst = APPLY ? out + (int64_t)stream * L + n0 : nullptr;
+        const bool has_div = in_peak != nullptr;
+        const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
+        const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (len == kEqChunk) &&
+                         (!APPLY || (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        if (vec) {
+            for (int i = 0; i < kEqChunk; i += 4) {
+                float4 x = __ldg(reinterpret_cast<const float4 *>(src + i));
+                if (has_div) { x.x = x.x / div; x.y = x.y / div; x.z = x.z / div; x.w = x.w / div; }
+                float4 y;
+                y.x = (float)eq_step((double)x.x, cf, z0, z1);
+                y.y = (float)eq_step((double)x.y, cf, z0, z1);
+                y.z = (float)eq_step((double)x.z, cf, z0, z1);
+                y.w = (float)eq_step((double)x.w, cf, z0, z1);
+                if (APPLY) {
+                    *reinterpret_cast<float4 *>(dst + i) = y;
+                    pk = fmaxf(pk, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
+                }
+            }
+        } else {
+            for (int i = 0; i < len; ++i) {
+                float x = __ldg(src + i);
+                if (has_div) x = x / div;
+                const float y = (float)eq_step((double)x, cf, z0, z1);
+                if (APPLY) { dst[i] = y; pk = fmaxf(pk, fabsf(y)); }
+            }
+        }
+        if (!APPLY) {
+#pragma unroll
+            for (int s = 0; s < 6; ++s) { st[(int64_t)(2 * s) * K] = z0[s]; st[(int64_t)(2 * s + 1) * K] = z1[s]; }
+        }
+    }
+    if (APPLY && out_peak != nullptr) {
+        pk = warp_max(pk);
+        if ((threadIdx.x & 31) == 0) atomic_peak(out_peak, p, pk);
+    }
+}
+
+// One warp per stream: S[k+1] = M * S[k] + F[k], S[0] = 0, where M is the zero-input transition of
+// the 12-state cascade over one full chunk.  Lane i < 12 owns row i of M and component i of S.
+__global__ void __launch_bounds__(32) eq_stitch_kernel(int chs, int K, const double *coefs,
+                                                       const double *zs_final, double *init) {
+    __shared__ double Msm[kEqStates][kEqStates + 1];
+    const int stream = blockIdx.x;
+    const int p = stream / chs;
+    const int lane = threadIdx.x;
+    double cf[6][5];
+    eq_load_coefs(coefs, p, cf);
+    if (lane < kEqStates) {  // column `lane` of M: propagate the basis state e_lane for one chunk
+        double z0[6], z1[6];
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+            z0[s] = (lane == 2 * s) ? 1.0 : 0.0;
+            z1[s] = (lane == 2 * s + 1) ? 1.0 : 0.0;
+        }
+        for (int i = 0; i < kEqChunk; ++i) (void)eq_step(0.0, cf, z0, z1);
+#pragma unroll
+        for (int s = 0; s < 6; ++s) { Msm[2 * s][lane] = z0[s]; Msm[2 * s + 1][lane] = z1[s]; }
+    }
+    __syncwarp();
+    double row[kEqStates];
+    const int r = lane < kEqStates ? lane : 0;
+#pragma unroll
+    for (int j = 0; j < kEqStates; ++j) row[j] = Msm[r][j];
+    const double *F = zs_final + ((int64_t)stream * kEqStates + r) * K;
+    double *S = init + ((int64_t)stream * kEqStates + r) * K;
+    double s = 0.0;
+    double fnext = K > 0 ? F[0] : 0.0;
+    for (int k = 0; k < K; ++k) {
+        if (lane < kEqStates) S[k] = s;
+        const double f = fnext;
+        if (k + 1 < K) fnext = F[k + 1];
+        double a0 = f, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < kEqStates; j += 3) {
+            a0 = fma(row[j], __shfl_sync(0xffffffffu, s, j), a0);
+            a1 = fma(row[j + 1], __shfl_sync(0xffffffffu, s, j + 1), a1);
+            a2 = fma(row[j + 2], __shfl_sync(0xffffffffu, s, j + 2), a2);
+        }
+        s = a0 + (a1 + a2);
+    }
+}
+
+// --------------------------------------------------------------------- compressor
+constexpr int kCompBlock = 256;  // samples per warp iteration (8 per lane)
+
+// juce::dsp::Compressor<float> restated in oracle/dsp_oracle.c: oracle_compressor.
+__global__ void __launch_bounds__(32) compressor_kernel(SigView in, const float *in_peak, float *out,
+                                                        int chs, int64_t L, const CompParams *prm,
+                                                        unsigned *out_peak) {
+    __shared__ __align__(16) float a_s[kCompBlock];
+    __shared__ __align__(16) float env_s[kCompBlock];
+    const int stream = blockIdx.x;
+    const int p = stream / chs, c = stream - p * chs;
+    const int lane = threadIdx.x;
+    const CompParams q = prm[p];
+    const bool has_div = in_peak != nullptr;
+    const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
+    float *dst = out + (int64_t)stream * L;
+    float env = 0.0f, pk = 0.0f;
+    float x[8], xn[8];
+    auto fetch = [&](int64_t base, float (&v)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t n = base + j * 32 + lane;  // coalesced: lane-contiguous
+            v[j] = n < L ? load_in(in, p, c, n) : 0.0f;
+        }
+    };
+    fetch(0, xn);
+    for (int64_t base = 0; base < L; base += kCompBlock) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            x[j] = has_div ? xn[j] / div : xn[j];
+            a_s[j * 32 + lane] = fabsf(x[j]);
+        }
+        if (base + kCompBlock < L) fetch(base + kCompBlock, xn);  // in flight during the serial part
+        __syncwarp();
+        if (lane == 0) {
+            // serial ballistics: env = a + c*(env - a), c = a > env ? cteAT : cteRL
+#pragma unroll 4
+            for (int i = 0; i < kCompBlock; i += 4) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(a_s + i);
+                float4 e4;
+                float d, pa, pr;
+                d = __fsub_rn(env, a4.x); pa = __fmul_rn(q.cte_at, d); pr = __fmul_rn(q.cte_rl, d);
+                env = __fadd_rn(a4.x, (a4.x > env) ? pa : pr); e4.x = env;
+                d = __fsub_rn(env, a4.y); pa = __fmul_rn(q.cte_at, d); pr = __fmul_rn(q.cte_rl, d);
+                env = __fadd_rn(a4.y, (a4.y > env) ? pa : pr); e4.y = env;
+                d = __fsub_rn(env, a4.z); pa = __fmul_rn(q.cte_at, d); pr = __fmul_rn(q.cte_rl, d);
+                env = __fadd_rn(a4.z, (a4.z > env) ? pa : pr); e4.z = env;
+                d = __fsub_rn(env, a4.w); pa = __fmul_rn(q.cte_at, d); pr = __fmul_rn(q.cte_rl, d);
+                env = __fadd_rn(a4.w, (a4.w > env) ? pa : pr); e4.w = env;
+                *reinterpret_cast<float4 *>(env_s + i) = e4;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t n = base + j * 32 + lane;
+            const float e = env_s[j * 32 + lane];
+            const float g = (e < q.thr) ? 1.0f : powf(__fmul_rn(e, q.thr_inv), q.expo);
+            const float y = __fmul_rn(g, x[j]);
+            if (n < L) { dst[n] = y; pk = fmaxf(pk, fabsf(y)); }
+        }
+        __syncwarp();
+    }
+    if (out_peak != nullptr) {
+        pk = warp_max(pk);
+        if (lane == 0) atomic_peak(out_peak, p, pk);
+    }
+}
+
+// --------------------------------------------------------------------- distortion
+__global__ void __launch_bounds__(256) distortion_kernel(SigView in, const float *in_peak, float *out,
+                                                         int chs, int64_t L, const DistParams *prm,
+                                                         unsigned *out_peak) {
+    const int stream = blockIdx.y;
+    const int p = stream / chs, c = stream - p * chs;
+    const DistParams q = prm[p];
+    const bool has_div = in_peak != nullptr;
+    const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
+    float pk = 0.0f;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.x * blockDim.x) {
+        float x = load_in(in, p, c, n);
+        if (has_div) x = x / div;
+        const float y = __fmul_rn(tanhf(__fmul_rn(x, q.drive)), q.out_gain);
+        out[(int64_t)stream * L + n] = y;
+        pk = fmaxf(pk, fabsf(y));
+    }
+    if (out_peak != nullptr) {
+        pk = warp_max(pk);
+        if ((threadIdx.x & 31) == 0) atomic_peak(out_peak, p, pk);
+    }
+}
+
+// -------------------------------------------------------------------------- delay
+// line[n] = x[n] + fb*line[n-d];  y[n] = dry*x[n] + mix*line[n-d]   (oracle_delay)
+__global__ void __launch_bounds__(256) delay_kernel(SigView in, const float *in_peak, float *out, int chs,
+                                                    int64_t L, const DelayParams *prm,
+                                                    unsigned *out_peak) {
+    const int stream = blockIdx.y;
+    const int p = stream / chs, c = stream - p * chs;
+    const DelayParams q = prm[p];
+    const bool has_div = in_peak != nullptr;
+    const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    float pk = 0.0f;
+    if (r < q.d) {
+        float prev = 0.0f;
+        for (int64_t n = r; n < L; n += q.d) {
+            float x = load_in(in, p, c, n);
+            if (has_div) x = x / div;
+            const float o = prev;
+            prev = __fadd_rn(x, __fmul_rn(q.feedback, o));
+            const float y = __fadd_rn(__fmul_rn(q.dry, x), __fmul_rn(q.mix, o));
+            out[(int64_t)stream * L + n] = y;
+            pk = fmaxf(pk, fabsf(y));
+        }
+    }
+    if (out_peak != nullptr) {
+        pk = warp_max(pk);
+        if ((threadIdx.x & 31) == 0) atomic_peak(out_peak, p, pk);
+    }
+}
+
+// ------------------------------------------------------------------------- reverb
+// JUCE_UNDENORMALISE on x86: x += 0.1f; x -= 0.1f
+__device__ __forceinline__ float undenorm(float v) { return __fsub_rn(__fadd_rn(v, 0.1f), 0.1f); }
+
+constexpr int kRevMaxSeg = 8;  // samples per lane per block (block <= 256)
+
+// juce::Reverb (Freeverb) restated in oracle/dsp_oracle.c: oracle_reverb.  NCH = 2: processStereo,
+// one CTA per candidate; NCH = 1: processMono, one CTA per (candidate, channel).
+template <int NCH>
+__global__ void __launch_bounds__(NCH * 256) reverb_kernel(SigView in, const float *in_peak, float *out,
+                                                           int chs, int64_t L, ReverbGeom g,
+                                                           const ReverbParams *prm, unsigned *out_peak) {
+    extern __shared__ float sm[];
+    float *ring = sm;
+    float *mixin = sm + g.total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int inst = blockIdx.x;
+    const int p = NCH == 2 ? inst : inst / chs;
+    const int c0 = NCH == 2 ? 0 : inst - p * chs;
+    const int B = g.block;
+    const int seg = B >> 5;
+    for (int i = tid; i < g.total; i += blockDim.x) ring[i] = 0.0f;
+    const ReverbParams q = prm[p];
+    const bool has_div = in_peak != nullptr;
+    const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
+    const float keep = __fsub_rn(1.0f, q.damp);
+
+    // phase-1 role: thread -> (sample nloc, channel c)
+    const int c = NCH == 2 ? (tid & 1) : 0;
+    const int nloc = NCH == 2 ? (tid >> 1) : tid;
+    const bool p1 = tid < NCH * B;
+    int cb[8], ab[4];  // ring positions of sample n0 for the 8 combs / 4 all-passes of channel c
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cb[j] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ab[j] = 0;
+    // comb role: warp -> (channel cc, comb j)
+    const int cc = warp >> 3, cj = warp & 7;
+    const bool comb_role = warp < NCH * 8;
+    const int csize = g.comb_size[comb_role ? cc : 0][cj];
+    float *cring = ring + g.comb_off[comb_role ? cc : 0][cj];
+    int mycb = 0;
+    float fstore = 0.0f;  // comb filterstore after the previous block
+    float dpow = 1.0f;    // damp^seg
+    for (int i = 0; i < seg; ++i) dpow = __fmul_rn(dpow, q.damp);
+
+    float *dst = out + ((int64_t)p * chs + (NCH == 2 ? c : c0)) * L;
+    const int cin = NCH == 2 ? c : c0;
+    float pk = 0.0f;
+    float xnext = (p1 && nloc < L) ? load_in(in, p, cin, nloc) : 0.0f;
+    __syncthreads();
+
+    for (int64_t n0 = 0; n0 < L; n0 += B) {
+        const int nb = (int)min((int64_t)B, L - n0);
+        if (p1) {
+            const bool act = nloc < nb;
+            float xin = xnext;
+            if (has_div) xin = xin / div;
+            {   // prefetch the next block's sample; consumed after the comb phase
+                const int64_t nn = n0 + B + nloc;
+                xnext = nn < L ? load_in(in, p, cin, nn) : 0.0f;
+            }
+            float inp;
+            if (NCH == 2) {
+                const float other = __shfl_xor_sync(0xffffffffu, xin, 1);
+                inp = __fmul_rn(__fadd_rn(xin, other), 0.015f);
+            } else {
+                inp = __fmul_rn(xin, 0.015f);
+            }
+            if (c == 0 && act) mixin[nloc] = inp;
+            float v = 0.0f;  // sum of the 8 comb outputs (delayed samples: independent of this block)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int pos = cb[j] + nloc;
+                const int sz = g.comb_size[c][j];
+                if (pos >= sz) pos -= sz;
+                v = __fadd_rn(v, ring[g.comb_off[c][j] + pos]);
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {  // series all-passes: lag >= block, so sample-parallel
+                int pos = ab[s] + nloc;
+                const int sz = g.ap_size[c][s];
+                if (pos >= sz) pos -= sz;
+                float *slot = ring + g.ap_off[c][s] + pos;
+                const float bv = *slot;
+                const float t = undenorm(__fadd_rn(v, __fmul_rn(bv, 0.5f)));
+                if (act) *slot = t;
+                v = __fsub_rn(bv, v);
+            }
+            float y;
+            if (NCH == 2) {
+                const float vo = __shfl_xor_sync(0xffffffffu, v, 1);
+                y = __fadd_rn(__fadd_rn(__fmul_rn(v, q.wet1), __fmul_rn(vo, q.wet2)), __fmul_rn(xin, q.dry));
+            } else {
+                y = __fadd_rn(__fmul_rn(v, q.wet1), __fmul_rn(xin, q.dry));
+            }
+            if (act) { dst[n0 + nloc] = y; pk = fmaxf(pk, fabsf(y)); }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cb[j] += B; if (cb[j] >= g.comb_size[c][j]) cb[j] -= g.comb_size[c][j]; }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { ab[s] += B; if (ab[s] >= g.ap_size[c][s]) ab[s] -= g.ap_size[c][s]; }
+        }
+        __syncthreads();
+        if (comb_role) {
+            const int i0 = lane * seg;
+            float o[kRevMaxSeg];
+            int pos0 = mycb + i0;
+            if (pos0 >= csize) pos0 -= csize;
+#pragma unroll
+            for (int i = 0; i < kRevMaxSeg; ++i) {
+                int pos = pos0 + i;
+                if (pos >= csize) pos -= csize;
+                o[i] = (i < seg) ? cring[pos] : 0.0f;
+            }
+            float z = 0.0f;  // zero-state response of the damping one-pole over my segment
+#pragma unroll
+            for (int i = 0; i < kRevMaxSeg; ++i)
+                if (i < seg) z = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(z, q.damp)));
+            float A = dpow, Bv = z;  // affine map of my segment: s -> A*s + Bv; inclusive scan
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float Ap = __shfl_up_sync(0xffffffffu, A, d);
+                const float Bp = __shfl_up_sync(0xffffffffu, Bv, d);
+                if (lane >= d) { Bv = fmaf(Bp, A, Bv); A = A * Ap; }
+            }
+            const float s_out = fmaf(A, fstore, Bv);
+            float s = __shfl_up_sync(0xffffffffu, s_out, 1);
+            if (lane == 0) s = fstore;
+#pragma unroll
+            for (int i = 0; i < kRevMaxSeg; ++i) {
+                if (i < seg) {
+                    s = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(s, q.damp)));
+                    const float t = undenorm(__fadd_rn(mixin[i0 + i], __fmul_rn(s, q.fb)));
+                    int pos = pos0 + i;
+                    if (pos >= csize) pos -= csize;
+                    if (i0 + i < nb) cring[pos] = t;
+                }
+            }
+            fstore = __shfl_sync(0xffffffffu, s, 31);
+            mycb += B;
+            if (mycb >= csize) mycb -= csize;
+        }
+        __syncthreads();
+    }
+    if (out_peak != nullptr) {
+        pk = warp_max(pk);
+        if (lane == 0) atomic_peak(out_peak, p, pk);
+    }
+}
+
+// ------------------------------------------------------------------- copy / peak
+__global__ void __launch_bounds__(256) copy_kernel(SigView in, const float *in_peak, float *out, int chs,
+                                                   int64_t L, unsigned *out_peak) {
+    const int stream = blockIdx.y;
+    const int p = stream / chs, c = stream - p * chs;
+    const bool has_div = in_peak != nullptr;
+    const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
+    float pk = 0.0f;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.x * blockDim.x) {
+        float x = load_in(in, p, c, n);
+        if (has_div) x = x / div;
+        if (out != nullptr) out[(int64_t)stream * L + n] = x;
+        pk = fmaxf(pk, fabsf(x));
+    }
+    if (out_peak != nullptr) {
+        pk = warp_max(pk);
+        if ((threadIdx.x & 31) == 0) atomic_peak(out_peak, p, pk);
+    }
+}
+
+__global__ void __launch_bounds__(256) normalize_kernel(const float *x, const unsigned *peak, float *y,
+                                                        int chs, int64_t L) {
+    const int stream = blockIdx.y;
+    const int p = stream / chs;
+    const float div = fmaxf(__uint_as_float(peak[p]), 1e-8f);
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.x * blockDim.x)
+        y[(int64_t)stream * L + n] = x[(int64_t)stream * L + n] / div;
+}
+
+inline int grid_for(int64_t L, int threads, int streams) {
+    // enough CTAs to fill 148 SMs a few times over without exceeding the work
+    int64_t want = (L + threads - 1) / threads;
+    int64_t cap = (148 * 16 + streams - 1) / streams;
+    if (cap < 1) cap = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace
+
+size_t eq_scratch_doubles(int P, int chs, int64_t L) {
+    const int64_t K = (L + kEqChunk - 1) / kEqChunk;
+    return (size_t)P * chs * kEqStates * K;
+}
+
+cudaError_t launch_eq(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
+                      int64_t L, const double *coefs, double *scratch_f, double *scratch_s,
+                      unsigned *out_peak, int *launches) {
+    const int K = (int)((L + kEqChunk - 1) / kEqChunk);
+    const int streams = P * chs;
+    dim3 grid((K + 127) / 128, streams);
+    eq_chunk_kernel<false><<<grid, 128, 0, st>>>(in, in_peak, nullptr, chs, L, K, coefs, scratch_f, nullptr);
+    eq_stitch_kernel<<<streams, 32, 0, st>>>(chs, K, coefs, scratch_f, scratch_s);
+    eq_chunk_kernel<true><<<grid, 128, 0, st>>>(in, in_peak, out, chs, L, K, coefs, scratch_s, out_peak);
+    *launches += 3;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compressor(cudaStream_t st, SigView in, const float *in_peak, float *out, int P,
+                              int chs, int64_t L, const CompParams *prm, unsigned *out_peak,
+                              int *launches) {
+    compressor_kernel<<<P * chs, 32, 0, st>>>(in, in_peak, out, chs, L, prm, out_peak);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_distortion(cudaStream_t st, SigView in, const float *in_peak, float *out, int P,
+                              int chs, int64_t L, const DistParams *prm, unsigned *out_peak,
+                              int *launches) {
+    dim3 grid(grid_for(L, 256, P * chs), P * chs);
+    distortion_kernel<<<grid, 256, 0, st>>>(in, in_peak, out, chs, L, prm, out_peak);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_delay(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
+                         int64_t L, const DelayParams *prm, int max_d, unsigned *out_peak,
+                         int *launches) {
+    dim3 grid((max_d + 255) / 256, P * chs);
+    delay_kernel<<<grid, 256, 0, st>>>(in, in_peak, out, chs, L, prm, out_peak);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+void reverb_geometry(double sample_rate, ReverbGeom *g) {
+    static const int comb_t[8] = {1116, 1188, 1277, 1356, 1422, 1491, 1557, 1617};
+    static const int ap_t[4] = {556, 441, 341, 225};
+    const int isr = (int)sample_rate;
+    int off = 0, min_ap = 1 << 30;
+    for (int c = 0; c < 2; ++c) {
+        for (int j = 0; j < 8; ++j) {
+            g->comb_size[c][j] = (int)(((int64_t)isr * (comb_t[j] + (c ? 23 : 0))) / 44100);
+            g->comb_off[c][j] = off;
+            off += g->comb_size[c][j];
+        }
+        for (int j = 0; j < 4; ++j) {
+            g->ap_size[c][j] = (int)(((int64_t)isr * (ap_t[j] + (c ? 23 : 0))) / 44100);
+            g->ap_off[c][j] = off;
+            off += g->ap_size[c][j];
+            if (g->ap_size[c][j] < min_ap) min_ap = g->ap_size[c][j];
+        }
+    }
+    g->total = off;
+    int b = (min_ap / 32) * 32;
+    if (b > 256) b = 256;
+    g->block = b;
+}
+
+cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
+                          int stereo, int64_t L, const ReverbGeom &g, const ReverbParams *prm,
+                          unsigned *out_peak, int *launches) {
+    if (g.block < 32) return cudaErrorInvalidValue;  // sample rate too low for the block scheme
+    const size_t smem = (size_t)(g.total + g.block) * sizeof(float);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e;
+    if (stereo) {
+        e = cudaFuncSetAttribute(reverb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        reverb_kernel<2><<<P, 512, smem, st>>>(in, in_peak, out, 2, L, g, prm, out_peak);
+    } else {
+        e = cudaFuncSetAttribute(reverb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        reverb_kernel<1><<<P * chs, 256, smem, st>>>(in, in_peak, out, chs, L, g, prm, out_peak);
+    }
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_copy(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
+                        int64_t L, unsigned *out_peak, int *launches) {
+    dim3 grid(grid_for(L, 256, P * chs), P * chs);
+    copy_kernel<<<grid, 256, 0, st>>>(in, in_peak, out, chs, L, out_peak);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peak(cudaStream_t st, SigView in, int P, int chs, int64_t L, unsigned *peak,
+                        int *launches) {
+    return launch_copy(st, in, nullptr, nullptr, P, chs, L, peak, launches);
+}
+
+cudaError_t launch_normalize(cudaStream_t st, const float *x, const unsigned *peak, float *y, int P,
+                             int chs, int64_t L, int *launches) {
+    dim3 grid(grid_for(L, 256, P * chs), P * chs);
+    normalize_kernel<<<grid, 256, 0, st>>>(x, peak, y, chs, L);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace stito
