@@ -16,6 +16,8 @@
 //   delay       lag-d feedback: the d residue classes are independent serial chains.
 // All float arithmetic uses explicit _rn intrinsics where the oracle (compiled with
 // -ffp-contract=off) rounds each operation separately.
+#include <cstdlib>
+
 #include "stito_internal.h"
 
 namespace stito {
@@ -173,67 +175,134 @@ __global__ void __launch_bounds__(32) eq_stitch_kernel(int chs, int K, const dou
 }
 
 // --------------------------------------------------------------------- compressor
-constexpr int kCompBlock = 256;  // samples per warp iteration (8 per lane)
+constexpr int kCompBlock = 256;  // samples per pipeline block (8 per lane of the IO warp)
+constexpr int kCompBufs = 4;     // blocks in flight between the IO warp and the serial lane
+
+__device__ __forceinline__ uint32_t cvta_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cvta_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cvta_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(cvta_smem(bar)), "r"(parity) : "memory");
+    }
+}
+
+constexpr int kCompIoWarps = 4;  // warps doing loads / gain computer / stores
 
 // juce::dsp::Compressor<float> restated in oracle/dsp_oracle.c: oracle_compressor.
-__global__ void __launch_bounds__(32) compressor_kernel(SigView in, const float *in_peak, float *out,
-                                                        int chs, int64_t L, const CompParams *prm,
-                                                        unsigned *out_peak) {
-    __shared__ __align__(16) float a_s[kCompBlock];
-    __shared__ __align__(16) float env_s[kCompBlock];
+// Five warps per stream: warps 1-4 (IO) stage |x| blocks into shared memory, and later apply the gain
+// computer (powf) and write the output; lane 0 of warp 0 runs nothing but the ballistics recurrence
+//     env = a + c*(env - a),  c = a > env ? cteAT : cteRL
+// over the staged blocks, so the only thing on the critical path is that recurrence.
+// EXACT = true evaluates it in the oracle's operation order (sub, mul, add: bit-identical envelope, 4
+// dependent ops per sample); EXACT = false uses the algebraically equal form
+//     env = a > env ? fma(cteAT, env, (1-cteAT)*a) : fma(cteRL, env, (1-cteRL)*a)
+// (2 dependent ops per sample; the envelope differs from the oracle's by float rounding only).
+template <bool EXACT>
+__global__ void __launch_bounds__(32 * (1 + kCompIoWarps)) compressor_kernel(SigView in, const float *in_peak,
+                                                                             float *out, int chs, int64_t L,
+                                                                             const CompParams *prm,
+                                                                             unsigned *out_peak) {
+    __shared__ __align__(16) float x_s[kCompBufs][kCompBlock];
+    __shared__ __align__(16) float a_s[kCompBufs][kCompBlock + 4];  // +4: the serial lane prefetches one quad ahead
+    __shared__ __align__(16) float env_s[kCompBufs][kCompBlock];
+    __shared__ uint64_t full[kCompBufs], ready[kCompBufs];
     const int stream = blockIdx.x;
     const int p = stream / chs, c = stream - p * chs;
-    const int lane = threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const CompParams q = prm[p];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kCompBufs; ++i) { mbar_init(&full[i], kCompIoWarps); mbar_init(&ready[i], 1); }
+    }
+    __syncthreads();
+    const int nblk = (int)((L + kCompBlock - 1) / kCompBlock);
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---------------- serial ballistics
+            float env = 0.0f;
+            const float ka = __fsub_rn(1.0f, q.cte_at), kr = __fsub_rn(1.0f, q.cte_rl);
+            for (int b = 0; b < nblk; ++b) {
+                const int buf = b % kCompBufs;
+                mbar_wait(&full[buf], (b / kCompBufs) & 1);
+                const float4 *a4p = reinterpret_cast<const float4 *>(a_s[buf]);
+                float4 *e4p = reinterpret_cast<float4 *>(env_s[buf]);
+                float4 nxt = a4p[0];
+#pragma unroll 4
+                for (int i = 0; i < kCompBlock / 4; ++i) {
+                    const float4 a4 = nxt;
+                    nxt = a4p[i + 1];  // software prefetch (the row has 4 floats of padding)
+                    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                    float ev[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float a = av[j];
+                        if (EXACT) {
+                            const float d = __fsub_rn(env, a);
+                            const float pa = __fmul_rn(q.cte_at, d), pr = __fmul_rn(q.cte_rl, d);
+                            env = __fadd_rn(a, (a > env) ? pa : pr);
+                        } else {
+                            const float ea = __fmaf_rn(q.cte_at, env, __fmul_rn(ka, a));
+                            const float er = __fmaf_rn(q.cte_rl, env, __fmul_rn(kr, a));
+                            env = (a > env) ? ea : er;
+                        }
+                        ev[j] = env;
+                    }
+                    e4p[i] = make_float4(ev[0], ev[1], ev[2], ev[3]);
+                }
+                mbar_arrive(&ready[buf]);
+            }
+        }
+        return;
+    }
+    // ---------------- IO warps: thread t owns samples t and t + 128 of every block (only ever touches
+    // its own slots of x_s / a_s / env_s, so IO threads need no barrier among themselves)
+    const int t = threadIdx.x - 32;
+    constexpr int kIoThreads = 32 * kCompIoWarps, kPer = kCompBlock / kIoThreads;
     const bool has_div = in_peak != nullptr;
     const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
     float *dst = out + (int64_t)stream * L;
-    float env = 0.0f, pk = 0.0f;
-    float x[8], xn[8];
-    auto fetch = [&](int64_t base, float (&v)[8]) {
+    float pk = 0.0f;
+    auto stage = [&](int b) {
+        const int buf = b % kCompBufs;
+        const int64_t base = (int64_t)b * kCompBlock;
+        float v[kPer];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int64_t n = base + j * 32 + lane;  // coalesced: lane-contiguous
+        for (int j = 0; j < kPer; ++j) {
+            const int64_t n = base + j * kIoThreads + t;  // coalesced
             v[j] = n < L ? load_in(in, p, c, n) : 0.0f;
         }
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const float x = has_div ? v[j] / div : v[j];
+            x_s[buf][j * kIoThreads + t] = x;
+            a_s[buf][j * kIoThreads + t] = fabsf(x);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[buf]);
     };
-    fetch(0, xn);
-    for (int64_t base = 0; base < L; base += kCompBlock) {
+    for (int b = 0; b < kCompBufs - 1 && b < nblk; ++b) stage(b);
+    for (int b = 0; b < nblk; ++b) {
+        if (b + kCompBufs - 1 < nblk) stage(b + kCompBufs - 1);  // refills the buffer finalised last iteration
+        const int buf = b % kCompBufs;
+        mbar_wait(&ready[buf], (b / kCompBufs) & 1);
+        const int64_t base = (int64_t)b * kCompBlock;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            x[j] = has_div ? xn[j] / div : xn[j];
-            a_s[j * 32 + lane] = fabsf(x[j]);
-        }
-        if (base + kCompBlock < L) fetch(base + kCompBlock, xn);  // in flight during the serial part
-        __syncwarp();
-        if (lane == 0) {
-            // serial ballistics: env = a + c*(env - a), c = a > env ? cteAT : cteRL
-#pragma unroll 4
-            for (int i = 0; i < kCompBlock; i += 4) {
-                const float4 a4 = *reinterpret_cast<const float4 *>(a_s + i);
-                float4 e4;
-                float d, pa, pr;
-                d = __fsub_rn(env, a4.x); pa = __fmul_rn(q.cte_at, d); pr = __fmul_rn(q.cte_rl, d);
-                env = __fadd_rn(a4.x, (a4.x > env) ? pa : pr); e4.x = env;
-                d = __fsub_rn(env, a4.y); pa = __fmul_rn(q.cte_at, d); pr = __fmul_rn(q.cte_rl, d);
-                env = __fadd_rn(a4.y, (a4.y > env) ? pa : pr); e4.y = env;
-                d = __fsub_rn(env, a4.z); pa = __fmul_rn(q.cte_at, d); pr = __fmul_rn(q.cte_rl, d);
-                env = __fadd_rn(a4.z, (a4.z > env) ? pa : pr); e4.z = env;
-                d = __fsub_rn(env, a4.w); pa = __fmul_rn(q.cte_at, d); pr = __fmul_rn(q.cte_rl, d);
-                env = __fadd_rn(a4.w, (a4.w > env) ? pa : pr); e4.w = env;
-                *reinterpret_cast<float4 *>(env_s + i) = e4;
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int64_t n = base + j * 32 + lane;
-            const float e = env_s[j * 32 + lane];
+        for (int j = 0; j < kPer; ++j) {
+            const int64_t n = base + j * kIoThreads + t;
+            const float e = env_s[buf][j * kIoThreads + t];
             const float g = (e < q.thr) ? 1.0f : powf(__fmul_rn(e, q.thr_inv), q.expo);
-            const float y = __fmul_rn(g, x[j]);
+            const float y = __fmul_rn(g, x_s[buf][j * kIoThreads + t]);
             if (n < L) { dst[n] = y; pk = fmaxf(pk, fabsf(y)); }
         }
-        __syncwarp();
     }
     if (out_peak != nullptr) {
         pk = warp_max(pk);
@@ -444,6 +513,149 @@ __global__ void __launch_bounds__(NCH * 256) reverb_kernel(SigView in, const flo
     }
 }
 
+// ---------------------------------------------------------------- reverb, fast path
+// The two channels of juce::Reverb share only the mono input sum and the final wet cross-mix, so the
+// comb/all-pass network of every (candidate, channel) runs in its own CTA and a trivial element-wise
+// kernel does the mix.  Delay lines are power-of-two rings (combs 2048, all-passes 1024 floats) indexed
+// with (n - delay) & mask: no per-ring position state and no wrap-around branches.  Same block scheme as
+// reverb_kernel: blocks of kRevFastBlock samples, phase 1 = comb outputs (delayed, independent of the
+// block) + sample-parallel all-passes, phase 2 = one warp per comb updates its ring (affine scan of the
+// damping one-pole across the 32 lanes).
+constexpr int kRevFastSeg = 7;
+constexpr int kRevFastBlock = 32 * kRevFastSeg;  // 224 <= shortest all-pass line at 44.1/48 kHz
+constexpr int kCombRing = 2048, kApRing = 1024;
+
+struct ReverbFastGeom {
+    int comb_delay[2][8];
+    int ap_delay[2][4];
+};
+
+// inst = (p, c): stereo != 0 -> input (l + r) * 0.015, tunings of channel c; else input x_c * 0.015, left tunings
+__global__ void __launch_bounds__(256) reverb_core_kernel(SigView in, const float *in_peak, float *wet, int chs,
+                                                          int stereo, int64_t L, ReverbFastGeom g,
+                                                          const ReverbParams *prm) {
+    extern __shared__ float sm[];
+    float *comb = sm;                        // [8][kCombRing]
+    float *ap = sm + 8 * kCombRing;          // [4][kApRing]
+    float *mixin = ap + 4 * kApRing;         // [kRevFastBlock]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int inst = blockIdx.x;
+    const int p = inst / chs, c = inst - p * chs;
+    const int tune = stereo ? c : 0;
+    for (int i = tid; i < 8 * kCombRing + 4 * kApRing; i += blockDim.x) sm[i] = 0.0f;
+    const ReverbParams q = prm[p];
+    const bool has_div = in_peak != nullptr;
+    const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
+    const float keep = __fsub_rn(1.0f, q.damp);
+    int cd[8], ad[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cd[j] = g.comb_delay[tune][j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ad[j] = g.ap_delay[tune][j];
+    const int my_delay = g.comb_delay[tune][warp];  // phase 2: warp w owns comb w
+    float *my_ring = comb + warp * kCombRing;
+    float fstore = 0.0f, dpow = 1.0f;
+#pragma unroll
+    for (int i = 0; i < kRevFastSeg; ++i) dpow = __fmul_rn(dpow, q.damp);
+
+    const bool p1 = tid < kRevFastBlock;
+    float *dst = wet + (int64_t)inst * L;
+    auto fetch = [&](int64_t n) -> float {
+        if (!p1 || n >= L) return 0.0f;
+        if (stereo) {
+            float l = load_in(in, p, 0, n), r = load_in(in, p, 1, n);
+            if (has_div) { l = l / div; r = r / div; }
+            return __fmul_rn(__fadd_rn(l, r), 0.015f);
+        }
+        float x = load_in(in, p, c, n);
+        if (has_div) x = x / div;
+        return __fmul_rn(x, 0.015f);
+    };
+    float in0 = fetch(tid), in1 = fetch((int64_t)kRevFastBlock + tid);  // two blocks of prefetch
+    __syncthreads();
+
+    for (int64_t n0 = 0; n0 < L; n0 += kRevFastBlock) {
+        const int nb = (int)min((int64_t)kRevFastBlock, L - n0);
+        const int nbase = (int)(n0 & (kCombRing * kApRing - 1));  // only the low bits matter for the masks
+        if (p1) {
+            const float inp = in0;
+            in0 = in1;
+            in1 = fetch(n0 + 2 * kRevFastBlock + tid);
+            const int n = nbase + tid;
+            mixin[tid] = inp;
+            float v = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v = __fadd_rn(v, comb[j * kCombRing + ((n - cd[j]) & (kCombRing - 1))]);
+            const bool act = tid < nb;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                float *slot_r = ap + s * kApRing + ((n - ad[s]) & (kApRing - 1));
+                const float bv = *slot_r;
+                const float t = undenorm(__fadd_rn(v, __fmul_rn(bv, 0.5f)));
+                if (act) ap[s * kApRing + (n & (kApRing - 1))] = t;
+                v = __fsub_rn(bv, v);
+            }
+            if (act) dst[n0 + tid] = v;
+        }
+        __syncthreads();
+        {   // phase 2: warp -> comb
+            const int i0 = lane * kRevFastSeg;
+            const int n = nbase + i0;
+            float o[kRevFastSeg];
+#pragma unroll
+            for (int i = 0; i < kRevFastSeg; ++i) o[i] = my_ring[(n + i - my_delay) & (kCombRing - 1)];
+            float z = 0.0f;
+#pragma unroll
+            for (int i = 0; i < kRevFastSeg; ++i) z = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(z, q.damp)));
+            float A = dpow, Bv = z;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float Ap = __shfl_up_sync(0xffffffffu, A, d);
+                const float Bp = __shfl_up_sync(0xffffffffu, Bv, d);
+                if (lane >= d) { Bv = fmaf(Bp, A, Bv); A = A * Ap; }
+            }
+            const float s_out = fmaf(A, fstore, Bv);
+            float s = __shfl_up_sync(0xffffffffu, s_out, 1);
+            if (lane == 0) s = fstore;
+#pragma unroll
+            for (int i = 0; i < kRevFastSeg; ++i) {
+                s = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(s, q.damp)));
+                const float t = undenorm(__fadd_rn(mixin[i0 + i], __fmul_rn(s, q.fb)));
+                if (i0 + i < nb) my_ring[(n + i) & (kCombRing - 1)] = t;
+            }
+            fstore = __shfl_sync(0xffffffffu, s, 31);
+        }
+        __syncthreads();
+    }
+}
+
+// l' = outl*wet1 + outr*wet2 + l*dry ; r' = outr*wet1 + outl*wet2 + r*dry   (mono: y = out*wet1 + x*dry)
+__global__ void __launch_bounds__(256) reverb_mix_kernel(SigView in, const float *in_peak, const float *wet,
+                                                         float *out, int chs, int stereo, int64_t L,
+                                                         const ReverbParams *prm, unsigned *out_peak) {
+    const int stream = blockIdx.y;
+    const int p = stream / chs, c = stream - p * chs;
+    const ReverbParams q = prm[p];
+    const bool has_div = in_peak != nullptr;
+    const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
+    const float *w_own = wet + (int64_t)stream * L;
+    const float *w_other = wet + (int64_t)(p * chs + (stereo ? 1 - c : c)) * L;
+    float pk = 0.0f;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.x * blockDim.x) {
+        float x = load_in(in, p, c, n);
+        if (has_div) x = x / div;
+        float y;
+        if (stereo) y = __fadd_rn(__fadd_rn(__fmul_rn(w_own[n], q.wet1), __fmul_rn(w_other[n], q.wet2)), __fmul_rn(x, q.dry));
+        else y = __fadd_rn(__fmul_rn(w_own[n], q.wet1), __fmul_rn(x, q.dry));
+        out[(int64_t)stream * L + n] = y;
+        pk = fmaxf(pk, fabsf(y));
+    }
+    if (out_peak != nullptr) {
+        pk = warp_max(pk);
+        if ((threadIdx.x & 31) == 0) atomic_peak(out_peak, p, pk);
+    }
+}
+
 // ------------------------------------------------------------------- copy / peak
 __global__ void __launch_bounds__(256) copy_kernel(SigView in, const float *in_peak, float *out, int chs,
                                                    int64_t L, unsigned *out_peak) {
@@ -504,7 +716,9 @@ cudaError_t launch_eq(cudaStream_t st, SigView in, const float *in_peak, float *
 cudaError_t launch_compressor(cudaStream_t st, SigView in, const float *in_peak, float *out, int P,
                               int chs, int64_t L, const CompParams *prm, unsigned *out_peak,
                               int *launches) {
-    compressor_kernel<<<P * chs, 32, 0, st>>>(in, in_peak, out, chs, L, prm, out_peak);
+    static const bool exact = [] { const char *e = getenv("STITO_COMP_EXACT"); return e && atoi(e) != 0; }();
+    if (exact) compressor_kernel<true><<<P * chs, 32 * (1 + kCompIoWarps), 0, st>>>(in, in_peak, out, chs, L, prm, out_peak);
+    else compressor_kernel<false><<<P * chs, 32 * (1 + kCompIoWarps), 0, st>>>(in, in_peak, out, chs, L, prm, out_peak);
     *launches += 1;
     return cudaGetLastError();
 }
@@ -553,11 +767,35 @@ void reverb_geometry(double sample_rate, ReverbGeom *g) {
 
 cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
                           int stereo, int64_t L, const ReverbGeom &g, const ReverbParams *prm,
-                          unsigned *out_peak, int *launches) {
+                          unsigned *out_peak, float *wet_scratch, int *launches) {
     if (g.block < 32) return cudaErrorInvalidValue;  // sample rate too low for the block scheme
+    cudaError_t e;
+    // fast path: power-of-two rings, one CTA per (candidate, channel) + mix kernel
+    int max_comb = 0, max_ap = 0, min_ap = 1 << 30;
+    for (int c = 0; c < 2; ++c) {
+        for (int j = 0; j < 8; ++j) max_comb = g.comb_size[c][j] > max_comb ? g.comb_size[c][j] : max_comb;
+        for (int j = 0; j < 4; ++j) {
+            max_ap = g.ap_size[c][j] > max_ap ? g.ap_size[c][j] : max_ap;
+            min_ap = g.ap_size[c][j] < min_ap ? g.ap_size[c][j] : min_ap;
+        }
+    }
+    if (wet_scratch != nullptr && max_comb <= kCombRing && max_ap <= kApRing && min_ap >= kRevFastBlock) {
+        ReverbFastGeom fg;
+        for (int c = 0; c < 2; ++c) {
+            for (int j = 0; j < 8; ++j) fg.comb_delay[c][j] = g.comb_size[c][j];
+            for (int j = 0; j < 4; ++j) fg.ap_delay[c][j] = g.ap_size[c][j];
+        }
+        const size_t smem = (size_t)(8 * kCombRing + 4 * kApRing + kRevFastBlock) * sizeof(float);
+        e = cudaFuncSetAttribute(reverb_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        reverb_core_kernel<<<P * chs, 256, smem, st>>>(in, in_peak, wet_scratch, chs, stereo, L, fg, prm);
+        dim3 grid(grid_for(L, 256, P * chs), P * chs);
+        reverb_mix_kernel<<<grid, 256, 0, st>>>(in, in_peak, wet_scratch, out, chs, stereo, L, prm, out_peak);
+        *launches += 2;
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t)(g.total + g.block) * sizeof(float);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e;
     if (stereo) {
         e = cudaFuncSetAttribute(reverb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

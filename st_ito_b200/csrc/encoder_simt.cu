@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) global_pool_kernel(const float *__restric
     y[idx] = mx + sum / (float)H;
 }
 
-// one warp per (row, output): out[b][e] = bias[e] + sum_k pooled[row][k] * w[k][e]
+// one warp per (item, head, output): out[b][e] = bias[e] + sum_k pooled[row][k] * w[e][k]
 __global__ void __launch_bounds__(256) heads_kernel(const float *__restrict__ pooled,
                                                     const float *__restrict__ w_mid,
                                                     const float *__restrict__ b_mid,
@@ -221,27 +221,28 @@ __global__ void __launch_bounds__(256) heads_kernel(const float *__restrict__ po
                                                     const float *__restrict__ b_side, int B, int chs,
                                                     int E, int Kdim, float *__restrict__ mid,
                                                     float *__restrict__ side) {
-    // thread per (b, head, e): coalesced over e for the [K][E] weights
-    const int64_t total = (int64_t)B * 2 * E;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int e = (int)(idx % E);
-    const int head = (int)((idx / E) % 2);
-    const int64_t b = idx / (2 * (int64_t)E);
-    float *dst = head ? side : mid;
-    if (chs == 1 && head == 1) return;  // filled below from mid by the head-0 thread
-    const float *row = pooled + (b * chs + head) * Kdim;
-    const float *w = head ? w_side : w_mid;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= (int64_t)B * 2 * E) return;
+    const int e = (int)(gw % E);
+    const int head = (int)((gw / E) % 2);
+    const int64_t b = gw / (2 * (int64_t)E);
+    if (chs == 1 && head == 1) return;  // mono: side = mid, written by the head-0 warp
+    const float4 *row = reinterpret_cast<const float4 *>(pooled + (b * chs + head) * Kdim);
+    const float4 *w = reinterpret_cast<const float4 *>((head ? w_side : w_mid) + (int64_t)e * Kdim);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int k = 0; k < Kdim; k += 4) {
-        a0 = fmaf(__ldg(row + k), __ldg(w + (int64_t)k * E + e), a0);
-        a1 = fmaf(__ldg(row + k + 1), __ldg(w + (int64_t)(k + 1) * E + e), a1);
-        a2 = fmaf(__ldg(row + k + 2), __ldg(w + (int64_t)(k + 2) * E + e), a2);
-        a3 = fmaf(__ldg(row + k + 3), __ldg(w + (int64_t)(k + 3) * E + e), a3);
+    for (int k = lane; k < Kdim / 4; k += 32) {
+        const float4 x = __ldg(row + k), y = __ldg(w + k);
+        a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1); a2 = fmaf(x.z, y.z, a2); a3 = fmaf(x.w, y.w, a3);
     }
-    const float v = ((a0 + a1) + (a2 + a3)) + __ldg((head ? b_side : b_mid) + e);
-    dst[b * E + e] = v;
-    if (chs == 1) side[b * E + e] = v;  // mono: side_embed = mid_embed (panns.py:273-274)
+    float v = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+        v += __ldg((head ? b_side : b_mid) + e);
+        (head ? side : mid)[b * E + e] = v;
+        if (chs == 1) side[b * E + e] = v;  // mono: side_embed = mid_embed (panns.py:273-274)
+    }
 }
 
 inline int blocks_for(int64_t total, int threads) {
@@ -294,7 +295,7 @@ cudaError_t launch_global_pool(cudaStream_t st, const float *x, float *y, int N,
 
 cudaError_t launch_heads(cudaStream_t st, const float *pooled, const EncoderDev &enc, int B, int chs,
                          float *mid, float *side, int *launches) {
-    const int64_t total = (int64_t)B * 2 * enc.embed_dim;
+    const int64_t total = (int64_t)B * 2 * enc.embed_dim * 32;  // one warp per output
     heads_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pooled, enc.fc_w[0], enc.fc_b[0],
                                                                  enc.fc_w[1], enc.fc_b[1], B, chs,
                                                                  enc.embed_dim, 2048, mid, side);

@@ -1,9 +1,584 @@
-// placeholder until the tcgen05 path lands
+// AFx-Rep encoder body on 5th-generation tensor cores (precision mode 1).
+//
+// Every 3x3 convolution with Cin >= 64 is an implicit GEMM   D[pixels, Cout] = A[pixels, 9*Cin] * B[9*Cin, Cout]
+// issued as tcgen05.mma (kind::f16, fp32 accumulation in TMEM) by one elected thread per CTA:
+//   * A is never materialised: for tap (kh, kw) and a 64-channel slab, the 128-pixel x 64-channel operand
+//     tile is ONE 4-D TMA box (C, W, H, N) at spatial offset (kh-1, kw-1); TMA's out-of-bounds zero fill
+//     IS the convolution's zero padding.  B tiles ([Cout][9*Cin], K-major) are 2-D TMA boxes.  Both land
+//     in shared memory in the 128-byte-swizzled K-major layout the UMMA descriptors expect.
+//   * error-compensated fp16x3: activations and (pre-scaled) weights are stored as hi + lo fp16 pairs and
+//     every K-slab issues  A_hi*B_hi  into the main fp32 accumulator and  A_lo*B_hi + A_hi*B_lo  into a second
+//     "correction" accumulator (TMEM columns [BN, 2BN)); the epilogue adds the two in fp32.  This keeps ~22
+//     mantissa bits of the operands (single-pass fp16/bf16 misses the 1e-4 embedding gate) and
+//     keeps the 2^-11-sized correction terms out of the main accumulator's truncating adds.  Activations are
+//     stored pre-multiplied by 2^6 (exact) so that their fp16 lo parts stay out of the subnormal range.
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
+//     (tcgen05.ld -> *unscale + bias -> ReLU -> fp16 hi/lo or fp32 NHWC store); smem full/empty mbarrier ring.
+// Replaces ConvBlock / Cnn14.forward's conv stack (st_ito/models/panns.py:25-80, 250-261).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstdio>
+#include <string>
+
 #include "encoder_tc.h"
+
 namespace stito {
-bool tc_available() { return false; }
-const char *tc_last_error() { return "tensor-core encoder not built"; }
-int tc_prepare_layer(const float *, int, int, ConvLayer *cl, std::vector<void *> *) { cl->w_hi = cl->w_lo = nullptr; cl->w_unscale = 1.0f; return 0; }
-int tc_encoder_forward(cudaStream_t, const EncoderDev &, TcWorkspace &, const float *, int, int, int, float *, int *, cudaEvent_t *) { return -1; }
-void tc_workspace_release(TcWorkspace *) {}
+
+namespace {
+
+thread_local std::string g_tc_err;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must fail loudly (trap -> cudaErrorLaunchFailure), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (!mbar_try_wait(bar, parity)) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) {  // 4 s
+            printf("libstito: mbarrier timeout (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+                   threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *m, uint64_t *bar, void *dst, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *m, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 operands, fp32 accumulate), one CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major, 128-byte swizzle, 128-byte rows, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30) = 0, SBO>>4 [32,46) = 64, version [46,48) = 1,
+//  layout_type [61,64) = 2 (SWIZZLE_128B)).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0,
+// A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr float kActScale = 64.0f;  // activations are stored as fp16 hi/lo of (value * 2^6)
+
+struct ConvTcParams {
+    const float *bias;   // [Cout]
+    float unscale;       // 2^-shift of the weight pre-scaling / kActScale of the input
+    float out_scale;     // kActScale for fp16-pair outputs
+    __half *out_hi, *out_lo;  // NHWC fp16 pair, or
+    float *out_f32;           // NHWC fp32 (when non-null)
+    int N, H, W, Cin, Cout;
+    int BW, BH, IPT;          // spatial tile: BW x BH pixels x IPT images (<= 128 rows)
+    int tilesW, tilesH;
+};
+
+constexpr int kTileM = 128;
+constexpr int kSlabK = 64;                       // fp16 elements = one 128-byte swizzle row
+constexpr int kABytes = kTileM * kSlabK * 2;     // 16 KB
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmAh,
+                                                            const __grid_constant__ CUtensorMap tmAl,
+                                                            const __grid_constant__ CUtensorMap tmBh,
+                                                            const __grid_constant__ CUtensorMap tmBl,
+                                                            const ConvTcParams p) {
+    constexpr int kBBytes = BN * kSlabK * 2;
+    constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * kStageBytes);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_group = p.tilesW * p.tilesH;
+    const int grp = blockIdx.x / tiles_per_group;
+    const int rem = blockIdx.x - grp * tiles_per_group;
+    const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+    const int n0 = grp * p.IPT, h0 = th * p.BH, w0 = tw * p.BW;
+    const int nt = blockIdx.y;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);  // [0, BN) main accumulator, [BN, 2BN) correction terms
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int cpt = p.Cin / kSlabK;  // channel slabs per tap
+    const int nslabs = 9 * cpt;
+    const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.IPT) * kSlabK * 2;
+    const uint32_t tx_bytes = 2 * a_box_bytes + 2 * kBBytes;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---------------- TMA producer
+            for (int s = 0; s < nslabs; ++s) {
+                const int stage = s % STAGES, it = s / STAGES;
+                if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                uint8_t *sb = smem + stage * kStageBytes;
+                mbar_expect_tx(&full[stage], tx_bytes);
+                const int tap = s / cpt, c0 = (s - tap * cpt) * kSlabK;
+                const int kh = tap / 3, kw = tap - kh * 3;
+                tma_load_4d(&tmAh, &full[stage], sb, c0, w0 + kw - 1, h0 + kh - 1, n0);
+                tma_load_4d(&tmAl, &full[stage], sb + kABytes, c0, w0 + kw - 1, h0 + kh - 1, n0);
+                tma_load_2d(&tmBh, &full[stage], sb + 2 * kABytes, tap * p.Cin + c0, nt * BN);
+                tma_load_2d(&tmBl, &full[stage], sb + 2 * kABytes + kBBytes, tap * p.Cin + c0, nt * BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---------------- MMA issuer
+            constexpr uint32_t idesc = make_idesc(kTileM, BN);
+            for (int s = 0; s < nslabs; ++s) {
+                const int stage = s % STAGES, it = s / STAGES;
+                mbar_wait(&full[stage], it & 1);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(smem + stage * kStageBytes);
+                const uint64_t a_hi = make_sdesc(sb), a_lo = make_sdesc(sb + kABytes);
+                const uint64_t b_hi = make_sdesc(sb + 2 * kABytes), b_lo = make_sdesc(sb + 2 * kABytes + kBBytes);
+#pragma unroll
+                for (int k = 0; k < kSlabK / 16; ++k)  // +32 B per K step of 16 inside the swizzle atom
+                    umma_f16(tmem_base + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < kSlabK / 16; ++k) umma_f16(tmem_base + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < kSlabK / 16; ++k)
+                    umma_f16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+            }
+            umma_commit(tmem_full);
+        }
+    } else {  // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int per_img = p.BW * p.BH;
+        const int img = m / per_img;
+        const int r = m - img * per_img;
+        const int rr = r / p.BW, cc = r - rr * p.BW;
+        const bool valid = img < p.IPT && (n0 + img) < p.N && (h0 + rr) < p.H && (w0 + cc) < p.W;
+        const int64_t pix = (((int64_t)(n0 + img) * p.H + (h0 + rr)) * p.W + (w0 + cc));
+        const int64_t obase = pix * p.Cout + (int64_t)nt * BN;
+        const float *bias = p.bias + nt * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32], u[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c), u);
+            tmem_ld_wait();
+            float y[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float acc = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                y[j] = fmaxf(fmaf(acc, p.unscale, __ldg(bias + c + j)), 0.0f) * p.out_scale;
+            }
+            if (valid) {
+                if (p.out_f32 != nullptr) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.out_f32 + obase + c);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                } else {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const __half h0v = __float2half_rn(y[2 * j]), h1v = __float2half_rn(y[2 * j + 1]);
+                        const __half l0v = __float2half_rn(y[2 * j] - __half2float(h0v));
+                        const __half l1v = __float2half_rn(y[2 * j + 1] - __half2float(h1v));
+                        hi[j] = (uint32_t)__half_as_ushort(h0v) | ((uint32_t)__half_as_ushort(h1v) << 16);
+                        lo[j] = (uint32_t)__half_as_ushort(l0v) | ((uint32_t)__half_as_ushort(l1v) << 16);
+                    }
+                    uint4 *dh = reinterpret_cast<uint4 *>(p.out_hi + obase + c);
+                    uint4 *dl = reinterpret_cast<uint4 *>(p.out_lo + obase + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------ SIMT helpers of the fp16x3 path
+// first conv (Cin == 1, K = 9: memory-bound, exact fp32): feat [N][H][W] -> hi/lo NHWC [N][H][W][64]
+__global__ void __launch_bounds__(256) tc_conv_first_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                            const float *__restrict__ bias, __half *__restrict__ yh,
+                                                            __half *__restrict__ yl, int N, int H, int W) {
+    __shared__ float ws[9][64];
+    __shared__ float bs[64];
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) ws[i / 64][i % 64] = w[i];
+    if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const int64_t total = (int64_t)N * H * W * 8;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(idx & 7);
+        const int64_t pix = idx >> 3;
+        const int wq = (int)(pix % W);
+        const int hq = (int)((pix / W) % H);
+        const int64_t n = pix / ((int64_t)W * H);
+        float v[9];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int hh = hq + kh - 1, ww = wq + kw - 1;
+                v[kh * 3 + kw] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + (n * H + hh) * W + ww) : 0.0f;
+            }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int c2 = 0; c2 < 4; ++c2) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                a0 = fmaf(v[t], ws[t][g * 8 + 2 * c2], a0);
+                a1 = fmaf(v[t], ws[t][g * 8 + 2 * c2 + 1], a1);
+            }
+            a0 = fmaxf(a0 + bs[g * 8 + 2 * c2], 0.f) * kActScale;
+            a1 = fmaxf(a1 + bs[g * 8 + 2 * c2 + 1], 0.f) * kActScale;
+            const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+            const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+            hi[c2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo[c2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        *reinterpret_cast<uint4 *>(yh + pix * 64 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(yl + pix * 64 + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// 2x2 average pool of the fp32 conv2 output -> fp16 hi/lo input of the next block
+__global__ void __launch_bounds__(256) tc_pool_split_kernel(const float *__restrict__ x, __half *__restrict__ yh,
+                                                            __half *__restrict__ yl, int N, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+    const int64_t total = (int64_t)N * Ho * Wo * C4;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % C4);
+        const int64_t pix = idx / C4;
+        const int wo = (int)(pix % Wo);
+        const int ho = (int)((pix / Wo) % Ho);
+        const int64_t n = pix / ((int64_t)Wo * Ho);
+        const float4 *src = reinterpret_cast<const float4 *>(x + ((n * H + 2 * ho) * W + 2 * wo) * C) + c4;
+        const float4 a = __ldg(src), b = __ldg(src + C4);
+        const float4 c = __ldg(src + (int64_t)W * C4), d = __ldg(src + (int64_t)W * C4 + C4);
+        constexpr float k = 0.25f * kActScale;  // exact powers of two
+        const float o[4] = {((a.x + b.x) + (c.x + d.x)) * k, ((a.y + b.y) + (c.y + d.y)) * k,
+                            ((a.z + b.z) + (c.z + d.z)) * k, ((a.w + b.w) + (c.w + d.w)) * k};
+        uint32_t hi[2], lo[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const __half h0 = __float2half_rn(o[2 * j]), h1 = __float2half_rn(o[2 * j + 1]);
+            const __half l0 = __float2half_rn(o[2 * j] - __half2float(h0)), l1 = __float2half_rn(o[2 * j + 1] - __half2float(h1));
+            hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        *reinterpret_cast<uint2 *>(yh + idx * 4) = make_uint2(hi[0], hi[1]);
+        *reinterpret_cast<uint2 *>(yl + idx * 4) = make_uint2(lo[0], lo[1]);
+    }
+}
+
+// ---------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int tc_fail(const char *what, const char *detail) {
+    g_tc_err = std::string(what) + ": " + detail;
+    return -1;
+}
+
+// activations: fp16 NHWC viewed as 4-D (C, W, H, N), box (64, BW, BH, IPT), 128B swizzle, zero OOB fill
+int make_act_map(CUtensorMap *m, const void *base, int N, int H, int W, int C, int BW, int BH, int IPT) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return tc_fail("cuTensorMapEncodeTiled", "driver entry point not found");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kSlabK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)IPT};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "CUresult %d for activation map N=%d H=%d W=%d C=%d box=(64,%d,%d,%d)", (int)r, N, H, W, C, BW, BH, IPT);
+        return tc_fail("cuTensorMapEncodeTiled", buf);
+    }
+    return 0;
+}
+
+// weights: fp16 [Cout][K] K-major, box (64, BN)
+int make_w_map(CUtensorMap *m, const void *base, int Cout, int K, int BN) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return tc_fail("cuTensorMapEncodeTiled", "driver entry point not found");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kSlabK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[128];
+        snprintf(buf, sizeof(buf), "CUresult %d for weight map Cout=%d K=%d BN=%d", (int)r, Cout, K, BN);
+        return tc_fail("cuTensorMapEncodeTiled", buf);
+    }
+    return 0;
+}
+
+template <int BN, int STAGES>
+int launch_conv_tc_t(cudaStream_t st, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh,
+                     const CUtensorMap &bl, const ConvTcParams &p, int mtiles) {
+    constexpr int smem = STAGES * (2 * kABytes + 2 * BN * kSlabK * 2) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return tc_fail("cudaFuncSetAttribute", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid(mtiles, p.Cout / BN);
+    conv3x3_tc_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ah, al, bh, bl, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return tc_fail("conv3x3_tc_kernel launch", cudaGetErrorString(e));
+    return 0;
+}
+
+int ws_ensure(TcWorkspace &ws, int i, size_t bytes) {
+    if (bytes <= ws.cap[i]) return 0;
+    if (ws.buf[i]) cudaFree(ws.buf[i]);
+    ws.buf[i] = nullptr;
+    ws.cap[i] = 0;
+    cudaError_t e = cudaMalloc(&ws.buf[i], bytes);
+    if (e != cudaSuccess) return tc_fail("cudaMalloc(workspace)", cudaGetErrorString(e));
+    ws.cap[i] = bytes;
+    return 0;
+}
+
+inline int blocks_for(int64_t total, int threads) {
+    int64_t b = (total + threads - 1) / threads;
+    const int64_t cap = 148 * 32;
+    return (int)(b < cap ? b : cap);
+}
+
+}  // namespace
+
+bool tc_available() { return true; }
+const char *tc_last_error() { return g_tc_err.c_str(); }
+
+int tc_prepare_layer(const float *wf, int cin, int cout, ConvLayer *cl, std::vector<void *> *owned) {
+    // pre-scale by a power of two so that the fp16 lo parts stay clear of the subnormal range
+    double mx = 0.0;
+    const size_t n = (size_t)9 * cin * cout;
+    for (size_t i = 0; i < n; ++i) mx = std::fmax(mx, std::fabs((double)wf[i]));
+    int shift = 0;
+    if (mx > 0) shift = -(int)std::ceil(std::log2(mx));  // max |w| * 2^shift in (0.5, 1]
+    if (shift > 14) shift = 14;
+    if (shift < -14) shift = -14;
+    const float scale = std::ldexp(1.0f, shift);
+    const int K = 9 * cin;
+    std::vector<__half> hi((size_t)cout * K), lo((size_t)cout * K);
+    for (int t = 0; t < 9; ++t)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int co = 0; co < cout; ++co) {
+                const float v = wf[((size_t)t * cin + ci) * cout + co] * scale;
+                const __half h = __float2half_rn(v);
+                const size_t o = (size_t)co * K + (size_t)t * cin + ci;
+                hi[o] = h;
+                lo[o] = __float2half_rn(v - __half2float(h));
+            }
+    void *dh = nullptr, *dl = nullptr;
+    cudaError_t e = cudaMalloc(&dh, hi.size() * sizeof(__half));
+    if (e != cudaSuccess) return tc_fail("cudaMalloc(weights)", cudaGetErrorString(e));
+    owned->push_back(dh);
+    e = cudaMalloc(&dl, lo.size() * sizeof(__half));
+    if (e != cudaSuccess) return tc_fail("cudaMalloc(weights)", cudaGetErrorString(e));
+    owned->push_back(dl);
+    e = cudaMemcpy(dh, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dl, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return tc_fail("cudaMemcpy(weights)", cudaGetErrorString(e));
+    cl->w_hi = dh;
+    cl->w_lo = dl;
+    cl->w_unscale = std::ldexp(1.0f, -shift);
+    return 0;
+}
+
+void tc_workspace_release(TcWorkspace *ws) {
+    for (int i = 0; i < 4; ++i) {
+        if (ws->buf[i]) cudaFree(ws->buf[i]);
+        ws->buf[i] = nullptr;
+        ws->cap[i] = 0;
+    }
+}
+
+// One conv layer on tensor cores: in (hi, lo) NHWC [N][H][W][Cin] -> out fp16 pair or fp32.
+static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, const __half *in_lo, __half *out_hi,
+                   __half *out_lo, float *out_f32, int N, int H, int W, int *launches) {
+    ConvTcParams p{};
+    p.bias = l.bias; p.unscale = l.w_unscale / kActScale;
+    p.out_scale = out_f32 ? 1.0f : kActScale;
+    p.out_hi = out_hi; p.out_lo = out_lo; p.out_f32 = out_f32;
+    p.N = N; p.H = H; p.W = W; p.Cin = l.cin; p.Cout = l.cout;
+    p.BW = W < 64 ? W : 64;
+    int bh = kTileM / p.BW;
+    if (bh > H) bh = H;
+    p.BH = bh;
+    int ipt = kTileM / (p.BW * p.BH);
+    if (ipt > N) ipt = N;
+    if (ipt < 1) ipt = 1;
+    p.IPT = ipt;
+    p.tilesW = (W + p.BW - 1) / p.BW;
+    p.tilesH = (H + p.BH - 1) / p.BH;
+    const int groups = (N + p.IPT - 1) / p.IPT;
+    const int mtiles = groups * p.tilesW * p.tilesH;
+    const int BN = l.cout >= 256 ? 256 : l.cout;
+    if (l.cin % kSlabK != 0 || l.cout % BN != 0 || (BN != 64 && BN != 128 && BN != 256))
+        return tc_fail("conv_tc", "unsupported channel counts");
+    CUtensorMap ah, al, bh_, bl;
+    if (make_act_map(&ah, in_hi, N, H, W, l.cin, p.BW, p.BH, p.IPT)) return -1;
+    if (make_act_map(&al, in_lo, N, H, W, l.cin, p.BW, p.BH, p.IPT)) return -1;
+    if (make_w_map(&bh_, l.w_hi, l.cout, 9 * l.cin, BN)) return -1;
+    if (make_w_map(&bl, l.w_lo, l.cout, 9 * l.cin, BN)) return -1;
+    int rc;
+    if (BN == 64) rc = launch_conv_tc_t<64, 4>(st, ah, al, bh_, bl, p, mtiles);
+    else if (BN == 128) rc = launch_conv_tc_t<128, 3>(st, ah, al, bh_, bl, p, mtiles);
+    else rc = launch_conv_tc_t<256, 2>(st, ah, al, bh_, bl, p, mtiles);
+    if (rc == 0) *launches += 1;
+    return rc;
+}
+
+int tc_encoder_forward(cudaStream_t st, const EncoderDev &enc, TcWorkspace &ws, const float *feat, int N, int T,
+                       int mel, float *pooled, int *launches, cudaEvent_t *ev) {
+    // workspace: [0],[1] = hi/lo activations A, [2] = hi+lo activations B (conv1 outputs), [3] = fp32 conv2 output
+    const size_t px0 = (size_t)N * T * mel;
+    if (ws_ensure(ws, 0, px0 * 16 * sizeof(__half))) return -1;  // block input (pooled) hi: largest is block 2, px0/4 x 64
+    if (ws_ensure(ws, 1, px0 * 16 * sizeof(__half))) return -1;  // lo
+    if (ws_ensure(ws, 2, 2 * px0 * 64 * sizeof(__half))) return -1;  // conv1 output hi | lo
+    if (ws_ensure(ws, 3, px0 * 64 * sizeof(float))) return -1;   // conv2 output fp32
+    __half *in_hi = (__half *)ws.buf[0], *in_lo = (__half *)ws.buf[1];
+    float *c2 = (float *)ws.buf[3];
+    int H = T, W = mel;
+    for (int b = 0; b < 6; ++b) {
+        const ConvLayer &l1 = enc.conv[2 * b], &l2 = enc.conv[2 * b + 1];
+        const size_t px = (size_t)N * H * W;
+        __half *m_hi = (__half *)ws.buf[2], *m_lo = m_hi + px * l1.cout;
+        if (ev) cudaEventRecord(ev[2 * b], st);
+        if (b == 0) {
+            tc_conv_first_kernel<<<blocks_for((int64_t)px * 8, 256), 256, 0, st>>>(feat, l1.w, l1.bias, m_hi, m_lo, N, H, W);
+            *launches += 1;
+        } else {
+            if (conv_tc(st, l1, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, launches)) return -1;
+        }
+        if (ev) cudaEventRecord(ev[2 * b + 1], st);
+        if (conv_tc(st, l2, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, launches)) return -1;
+        if (b < 5) {
+            const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (l2.cout / 4);
+            tc_pool_split_kernel<<<blocks_for(total, 256), 256, 0, st>>>(c2, in_hi, in_lo, N, H, W, l2.cout);
+            *launches += 1;
+            H /= 2;
+            W /= 2;
+        }
+    }
+    if (ev) cudaEventRecord(ev[12], st);
+    cudaError_t e = launch_global_pool(st, c2, pooled, N, H, W, 2048, launches);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return tc_fail("tc_encoder_forward", cudaGetErrorString(e));
+    return 0;
+}
+
 }  // namespace stito

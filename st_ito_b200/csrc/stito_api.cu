@@ -171,7 +171,7 @@ struct stito_handle {
     int n_fft = 2048, hop = 1024, n_mels = 128, embed_dim = 512;
 
     // work buffers
-    DevBuf audio[2], eq_f, eq_s, params, peaks, Wdev, feat, act[3], pooled, emb, fit, flags, xin;
+    DevBuf audio[2], wet, eq_f, eq_s, params, peaks, Wdev, feat, act[3], pooled, emb, fit, flags, xin;
     HostBuf hparams, hW;
     ReverbGeom rgeom{};
     TcWorkspace tcws;
@@ -237,16 +237,18 @@ void design_params(const stito_chain_desc &c, const double *W, int P, int D, uin
                 const double raw = d.w_index[k] >= 0 ? W[(size_t)p * D + d.w_index[k]] : d.fixed_raw[k];
                 v[k] = denorm(raw, rg[k]);
             }
-            uint8_t *slot = hp + ((size_t)f * P + p) * kParamSlot;
+            // effect f owns the block [f*P*kParamSlot, (f+1)*P*kParamSlot); inside it the kernels index a
+            // dense array of the effect's own parameter struct
+            uint8_t *block = hp + (size_t)f * P * kParamSlot;
             switch (d.kind) {
                 case STITO_FX_EQ: {
-                    double *cf = reinterpret_cast<double *>(slot);
+                    double *cf = reinterpret_cast<double *>(block) + (size_t)p * 30;
                     for (int s = 0; s < 6; ++s)
                         biquad_design(v[3 * s], v[3 * s + 1], v[3 * s + 2], fs, s == 0 ? 0 : (s == 5 ? 2 : 1), cf + 5 * s);
                     break;
                 }
                 case STITO_FX_COMPRESSOR: {  // oracle_compressor
-                    CompParams *q = reinterpret_cast<CompParams *>(slot);
+                    CompParams *q = reinterpret_cast<CompParams *>(block) + p;
                     const float thr_db = (float)v[0], ratio = (float)v[1], at = (float)v[2], rl = (float)v[3];
                     const double ef = -2.0 * M_PI * 1000.0 / fs;
                     q->cte_at = at < 1.0e-3f ? 0.0f : (float)std::exp(ef / (double)at);
@@ -257,14 +259,14 @@ void design_params(const stito_chain_desc &c, const double *W, int P, int D, uin
                     break;
                 }
                 case STITO_FX_DISTORTION: {  // oracle_distortion
-                    DistParams *q = reinterpret_cast<DistParams *>(slot);
+                    DistParams *q = reinterpret_cast<DistParams *>(block) + p;
                     const float dr = (float)v[0], og = (float)v[1];
                     q->drive = dr > -100.0f ? powf(10.0f, dr * 0.05f) : 0.0f;
                     q->out_gain = og > -100.0f ? powf(10.0f, og * 0.05f) : 0.0f;
                     break;
                 }
                 case STITO_FX_DELAY: {  // oracle_delay
-                    DelayParams *q = reinterpret_cast<DelayParams *>(slot);
+                    DelayParams *q = reinterpret_cast<DelayParams *>(block) + p;
                     const float ds = (float)v[0];
                     int dd = (int)((double)ds * fs);
                     if (dd < 1) dd = 1;
@@ -276,7 +278,7 @@ void design_params(const stito_chain_desc &c, const double *W, int P, int D, uin
                     break;
                 }
                 case STITO_FX_REVERB: {  // BasicReverb.process (effects.py:952-959) + oracle_reverb
-                    ReverbParams *q = reinterpret_cast<ReverbParams *>(slot);
+                    ReverbParams *q = reinterpret_cast<ReverbParams *>(block) + p;
                     const float room = (float)v[0], damping = (float)v[1];
                     const float wet_level = (float)v[2], dry_level = (float)(1 - v[2]), width = (float)v[3];
                     const float wet = wet_level * 3.0f;
@@ -340,7 +342,6 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
         const bool last = f == c.num_fx - 1;
         unsigned *opk = (last || c.normalize_stages) ? peaks + (size_t)f * P : nullptr;
         const uint8_t *slot = h->params.as<uint8_t>() + (size_t)f * P * kParamSlot;
-        // NB the slot stride is kParamSlot bytes for every effect kind
         switch (d.kind) {
             case STITO_FX_EQ: {
                 const size_t nd = eq_scratch_doubles(P, cur_chs, L);
@@ -361,7 +362,9 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
                 break;
             case STITO_FX_REVERB: {
                 const int stereo = (cur_chs == 2 && d.num_channels == 2) ? 1 : 0;
-                cudaError_t e = launch_reverb(st, cur, in_peak, out, P, cur_chs, stereo, L, h->rgeom, reinterpret_cast<const ReverbParams *>(slot), opk, launches);
+                CU(h->wet.ensure((size_t)P * cur_chs * L * sizeof(float)));
+                cudaError_t e = launch_reverb(st, cur, in_peak, out, P, cur_chs, stereo, L, h->rgeom,
+                                              reinterpret_cast<const ReverbParams *>(slot), opk, h->wet.as<float>(), launches);
                 if (e == cudaErrorInvalidValue) return fail(STITO_EINVAL, "reverb: unsupported sample rate %.1f", c.sample_rate);
                 CU(e);
                 break;
@@ -510,10 +513,7 @@ int stito_create(const stito_chain_desc *chain, const stito_encoder_weights *wts
             const float *w = hd ? wts->fc_side_w : wts->fc_mid_w;
             const float *b = hd ? wts->fc_side_b : wts->fc_mid_b;
             if (!w || !b) return bail(fail(STITO_EINVAL, "encoder weights: fc tensors are NULL"));
-            std::vector<float> wt((size_t)2048 * E);
-            for (int e = 0; e < E; ++e)
-                for (int k = 0; k < 2048; ++k) wt[(size_t)k * E + e] = w[(size_t)e * 2048 + k];
-            CUB(dev_alloc_copy(h, wt.data(), wt.size() * sizeof(float), (void **)&h->enc.fc_w[hd]));
+            CUB(dev_alloc_copy(h, w, (size_t)2048 * E * sizeof(float), (void **)&h->enc.fc_w[hd]));
             CUB(dev_alloc_copy(h, b, (size_t)E * sizeof(float), (void **)&h->enc.fc_b[hd]));
         }
         h->enc.embed_dim = E;
@@ -560,7 +560,7 @@ void stito_destroy(stito_handle *h) {
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     cudaDeviceSynchronize();
     for (void *p : h->owned) cudaFree(p);
-    DevBuf *bufs[] = {&h->input, &h->target, &h->audio[0], &h->audio[1], &h->eq_f, &h->eq_s, &h->params,
+    DevBuf *bufs[] = {&h->input, &h->target, &h->audio[0], &h->audio[1], &h->wet, &h->eq_f, &h->eq_s, &h->params,
                       &h->peaks, &h->Wdev, &h->feat, &h->act[0], &h->act[1], &h->act[2], &h->pooled,
                       &h->emb, &h->fit, &h->flags, &h->xin};
     for (DevBuf *b : bufs) b->release();

@@ -48,10 +48,10 @@ cudaError_t launch_delay(cudaStream_t st, SigView in, const float *in_peak, floa
                          int64_t L, const DelayParams *prm, int max_d, unsigned *out_peak,
                          int *launches);
 // stereo != 0: one joint stereo Freeverb per candidate (chs must be 2); else one mono Freeverb
-// per (candidate, channel).
+// per (candidate, channel).  wet_scratch: [P][chs][L] floats enabling the fast two-kernel path (nullable).
 cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
                           int stereo, int64_t L, const ReverbGeom &g, const ReverbParams *prm,
-                          unsigned *out_peak, int *launches);
+                          unsigned *out_peak, float *wet_scratch, int *launches);
 cudaError_t launch_copy(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
                         int64_t L, unsigned *out_peak, int *launches);
 // peak[i] = max |x[i, :, :]| as float bits (buffer must be zeroed first).
@@ -88,7 +88,7 @@ struct ConvLayer {
 };
 struct EncoderDev {
     ConvLayer conv[12];
-    float *fc_w[2];  // [2048][embed_dim] (transposed for coalesced reads)
+    float *fc_w[2];  // [embed_dim][2048] (reference layout)
     float *fc_b[2];
     int embed_dim;
 };

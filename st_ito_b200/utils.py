@@ -106,13 +106,15 @@ def load_param_model(ckpt_path: str = None, use_gpu: bool = False):
     return model
 
 
-def make_synthetic_param_model(seed: int = 0, bn_stats: bool = True, use_gpu: bool = False):
+def make_synthetic_param_model(seed: int = 0, bn_stats: bool = True, use_gpu: bool = False, conv_gain: float = 1.0):
     """AFx-Rep architecture with seeded random weights (no checkpoint is obtainable offline).
 
     Convolutions / heads use the reference's Xavier-uniform initialisers (panns.py:10-22); with
     ``bn_stats`` every BatchNorm gets non-trivial seeded affine parameters and running statistics so
-    that BatchNorm folding is exercised.  Same construction as oracle/cnn14.py:make_encoder, so the
-    two produce identical state_dicts for the same seed.
+    that BatchNorm folding is exercised.  ``conv_gain`` scales every convolution weight (gain 2 keeps
+    the input-dependent part of the activations alive through 12 ReLU layers, which Xavier gain 1 does
+    not).  Same construction as oracle/cnn14.py:make_encoder, so the two produce identical state_dicts
+    for the same arguments.
     """
     from .models.panns import AFX_REP_ARGS, Cnn14
 
@@ -123,6 +125,10 @@ def make_synthetic_param_model(seed: int = 0, bn_stats: bool = True, use_gpu: bo
         m = Cnn14(**AFX_REP_ARGS)
     finally:
         torch.random.set_rng_state(prev)
+    if conv_gain != 1.0:
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Conv2d):
+                mod.weight.data.mul_(conv_gain)
     if bn_stats:
         for mod in m.modules():
             if isinstance(mod, torch.nn.BatchNorm2d):

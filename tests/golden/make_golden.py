@@ -89,10 +89,13 @@ def golden_cnn14():
 
 
 def golden_fitness():
-    """P=8 EQ-only population, L=40000 stereo (>= 32 frames needed by five 2x2 pools after padding)."""
+    """P=8 EQ-only population, L=40000 stereo (>= 32 frames needed by five 2x2 pools after padding),
+    scored by the reference's Cnn14 with seeded weights (conv_gain=2) and centred heads
+    (oracle.cnn14.centre_heads): a well-conditioned ranking, see oracle.cnn14.make_encoder."""
     plugins, D, _ = eq_plugins()
     ref = panns.Cnn14(**cnn14.AFX_REP_ARGS).eval()
-    ref.load_state_dict(cnn14.make_encoder(seed=3, bn_stats=True).state_dict())
+    ref.load_state_dict(cnn14.make_encoder(seed=3, bn_stats=True, conv_gain=2.0).state_dict())
+    cnn14.centre_heads(ref)
     x = test_signal(2, 40000, seed=5)
     x = x / np.abs(x).max()
     w_star = np.random.RandomState(1234).rand(D)
@@ -112,14 +115,15 @@ def golden_fitness():
     f = torch.stack([-torch.cosine_similarity(oe[k], te[k], dim=-1) for k in oe]).mean(0).numpy()
     np.savez_compressed(os.path.join(HERE, "fitness.npz"), W=W, w_star=w_star, fitness=f,
                         argsort=np.argsort(f, kind="stable"), mid=oe["mid"].numpy(), side=oe["side"].numpy(),
-                        tgt_mid=te["mid"].numpy(), tgt_side=te["side"].numpy())
+                        tgt_mid=te["mid"].numpy(), tgt_side=te["side"].numpy(),
+                        bias_mid=ref.fc_mid.bias.detach().numpy(), bias_side=ref.fc_side.bias.detach().numpy())
 
 
 if __name__ == "__main__":
-    golden_biquad()
-    golden_eq()
-    golden_cnn14()
-    golden_fitness()
+    only = sys.argv[1:]
+    for fn in (golden_biquad, golden_eq, golden_cnn14, golden_fitness):
+        if not only or fn.__name__.replace("golden_", "") in only:
+            fn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

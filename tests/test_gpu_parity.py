@@ -41,6 +41,23 @@ def models():
     return ours, ref
 
 
+@pytest.fixture(scope="module")
+def models_centred():
+    """Seeded weights with conv_gain=2 and centred heads (oracle.cnn14.make_encoder / centre_heads): the
+    encoder output depends on the audio the way a trained one does, fitness spreads over O(1), and ranking
+    parity is meaningful; also the harder case for encoder precision (the common mode cancels)."""
+    from oracle import cnn14
+    from st_ito_b200.utils import make_synthetic_param_model
+
+    ours = make_synthetic_param_model(seed=3, bn_stats=True, conv_gain=2.0)
+    ref = cnn14.make_encoder(seed=3, bn_stats=True, conv_gain=2.0)
+    cnn14.centre_heads(ref)
+    with torch.no_grad():
+        ours.fc_mid.bias.copy_(ref.fc_mid.bias)
+        ours.fc_side.bias.copy_(ref.fc_side.bias)
+    return ours, ref
+
+
 def native_plugins(kinds, load=True):
     from st_ito_b200 import effects
     from st_ito_b200.style_transfer import load_plugins
@@ -244,17 +261,18 @@ def test_get_param_embeds_long_input(models, precision):
 
 # ------------------------------------------------------------------------------ population fitness
 @pytest.mark.parametrize("precision", [0, 1])
-def test_golden_fitness_and_ranking(models, golden_dir, oracle_dsp, precision):
+def test_golden_fitness_and_ranking(models_centred, golden_dir, oracle_dsp, precision):
     """Fixture made by the reference's process_audio + Cnn14: fitness values and the full ranking."""
     from st_ito_b200.engine import compile_chain
 
-    ours, _ = models
+    ours, _ = models_centred
+    g = np.load(os.path.join(golden_dir, "fitness.npz"))
+    np.testing.assert_allclose(ours.fc_mid.bias.detach().numpy(), g["bias_mid"], atol=2e-5)
     eng = ours.stito_engine()
     try:
         eng.set_precision(precision)
     except Exception:
         pytest.skip("tensor-core encoder not built")
-    g = np.load(os.path.join(golden_dir, "fitness.npz"))
     plugins, D, _ = native_plugins(["eq"])
     x = test_signal(2, 40000, seed=5)
     x = x / np.abs(x).max()
@@ -272,12 +290,12 @@ def test_golden_fitness_and_ranking(models, golden_dir, oracle_dsp, precision):
 
 @pytest.mark.parametrize("chain,chs,precision", [(["eq"], 1, 0), (["eq", "comp", "reverb"], 2, 0),
                                                  (["eq", "comp", "reverb"], 2, 1), (["eq"], 1, 1)])
-def test_eval_population_matches_oracle_evaluate(models, oracle_dsp, chain, chs, precision):
+def test_eval_population_matches_oracle_evaluate(models_centred, oracle_dsp, chain, chs, precision):
     """evaluate() end to end (pad-to-262144 policy included) against the oracle's restatement."""
     from oracle import cnn14
     from st_ito_b200.engine import compile_chain
 
-    ours, ref = models
+    ours, ref = models_centred
     eng = ours.stito_engine()
     try:
         eng.set_precision(precision)
@@ -306,14 +324,14 @@ def test_eval_population_matches_oracle_evaluate(models, oracle_dsp, chain, chs,
     assert rel_err(emb[1].numpy(), oe["side"].numpy()) < 1e-4
 
 
-def test_eval_population_properties_at_full_size(models):
+def test_eval_population_properties_at_full_size(models_centred):
     """BASELINE config-2 shape (10 s stereo, EQ+Comp+Reverb) where the oracle takes minutes:
     size-independent properties instead -- determinism, permutation equivariance, micro-batch
     invariance, and the target's own parameters scoring (numerically) -1."""
     from st_ito_b200.engine import compile_chain
     from st_ito_b200.style_transfer import process_audio
 
-    ours, _ = models
+    ours, _ = models_centred
     eng = ours.stito_engine()
     plugins, D, _ = native_plugins(["eq", "comp", "reverb"])
     L = 480000
