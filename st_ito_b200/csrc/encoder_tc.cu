@@ -7,19 +7,22 @@
 //     IS the convolution's zero padding.  B tiles ([Cout][9*Cin], K-major) are 2-D TMA boxes.  Both land
 //     in shared memory in the 128-byte-swizzled K-major layout the UMMA descriptors expect.
 //   * error-compensated fp16x3: activations and (pre-scaled) weights are stored as hi + lo fp16 pairs and
-//     every K-slab issues  A_hi*B_hi  into the main fp32 accumulator and  A_lo*B_hi + A_hi*B_lo  into a second
-//     "correction" accumulator (TMEM columns [BN, 2BN)); the epilogue adds the two in fp32.  This keeps ~22
-//     mantissa bits of the operands (single-pass fp16/bf16 misses the 1e-4 embedding gate) and
-//     keeps the 2^-11-sized correction terms out of the main accumulator's truncating adds.  Activations are
-//     stored pre-multiplied by 2^6 (exact) so that their fp16 lo parts stay out of the subnormal range.
-//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-//     (tcgen05.ld -> *unscale + bias -> ReLU -> fp16 hi/lo or fp32 NHWC store); smem full/empty mbarrier ring.
+//     every K-slab issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  into an fp32 TMEM accumulator: ~22 mantissa
+//     bits of each operand (single-pass fp16/bf16 misses the 1e-4 embedding gate).
+//     Activations are stored pre-multiplied by 2^6 (exact) so their fp16 lo parts stay out of the
+//     subnormal range.
+//   * the tensor core's fp32 accumulation truncates, so the K loop is chunked: each chunk of a few K-slabs
+//     accumulates in one half of a 2-deep TMEM ring and is then added, round-to-nearest, to fp32 register
+//     accumulators by the epilogue warps while the next chunk is being multiplied (see the kernel comment).
+//   * persistent CTAs (one per SM) walk the tile list; warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+//     issuer, warps 2-9 = drain/epilogue; smem full/empty and TMEM full/empty mbarrier rings.
 // Replaces ConvBlock / Cnn14.forward's conv stack (st_ito/models/panns.py:25-80, 250-261).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "encoder_tc.h"
@@ -147,135 +150,190 @@ struct ConvTcParams {
     int N, H, W, Cin, Cout;
     int BW, BH, IPT;          // spatial tile: BW x BH pixels x IPT images (<= 128 rows)
     int tilesW, tilesH;
+    int mtiles, ntiles;       // tile grid; the persistent CTAs walk tile = m + mtiles * n
+    int chunk_slabs;          // K-slabs accumulated inside TMEM before the fp32 drain (see below)
 };
 
 constexpr int kTileM = 128;
 constexpr int kSlabK = 64;                       // fp16 elements = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kSlabK * 2;     // 16 KB
+constexpr int kEpiWarps = 8;                     // 4 TMEM lane quarters x 2 column halves
+constexpr int kConvThreads = 32 * (2 + kEpiWarps);
+constexpr int kAccStages = 2;                    // TMEM accumulator ring
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent, warp-specialised implicit-GEMM convolution.
+//
+//   warp 0      TMA producer: for every tile and K-slab (tap, 64-channel slab) loads A_hi, A_lo (4-D boxes of
+//               the NHWC activations at the tap's spatial offset; out-of-bounds zero fill = conv padding) and
+//               B_hi, B_lo into a STAGES-deep shared-memory ring; runs ahead across tile boundaries.
+//   warp 1      MMA issuer: 12 tcgen05.mma per slab (A_lo*B_hi, A_hi*B_lo, A_hi*B_hi) into ONE fp32 TMEM
+//               accumulator.  The tensor core's fp32 accumulate truncates (round-toward-zero): over the
+//               1152 sequential adds of a K = 18432 layer that bias reaches ~5e-5 relative.  So the K loop
+//               is cut into chunks of `chunk_slabs` slabs; every chunk starts a fresh accumulator in the
+//               other half of a 2-deep TMEM ring ...
+//   warps 2-9   ... and the epilogue warps drain each finished chunk (tcgen05.ld) and add it to per-thread
+//               fp32 register accumulators with round-to-nearest on the CUDA cores while the next chunk is
+//               being multiplied.  After the last chunk: * unscale + bias, ReLU, fp16 hi/lo split (or fp32)
+//               and the NHWC store.  The drain of tile i's last chunk overlaps the MMAs of tile i+1.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmAh,
-                                                            const __grid_constant__ CUtensorMap tmAl,
-                                                            const __grid_constant__ CUtensorMap tmBh,
-                                                            const __grid_constant__ CUtensorMap tmBl,
-                                                            const ConvTcParams p) {
+__global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmAh,
+                                                                     const __grid_constant__ CUtensorMap tmAl,
+                                                                     const __grid_constant__ CUtensorMap tmBh,
+                                                                     const __grid_constant__ CUtensorMap tmBl,
+                                                                     const ConvTcParams p) {
     constexpr int kBBytes = BN * kSlabK * 2;
     constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    constexpr int kCols = BN / 2;  // accumulator columns owned by one epilogue thread
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * kStageBytes);
     uint64_t *empty = full + STAGES;
-    uint64_t *tmem_full = empty + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    uint64_t *acc_full = empty + STAGES;
+    uint64_t *acc_empty = acc_full + kAccStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + kAccStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_group = p.tilesW * p.tilesH;
-    const int grp = blockIdx.x / tiles_per_group;
-    const int rem = blockIdx.x - grp * tiles_per_group;
-    const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
-    const int n0 = grp * p.IPT, h0 = th * p.BH, w0 = tw * p.BW;
-    const int nt = blockIdx.y;
+    const int total_tiles = p.mtiles * p.ntiles;
+    const int cpt = p.Cin / kSlabK;  // channel slabs per tap
+    const int nslabs = 9 * cpt;
+    const int nchunks = (nslabs + p.chunk_slabs - 1) / p.chunk_slabs;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);  // [0, BN) main accumulator, [BN, 2BN) correction terms
+    if (warp == 1) tmem_alloc(tmem_slot, kAccStages * BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int cpt = p.Cin / kSlabK;  // channel slabs per tap
-    const int nslabs = 9 * cpt;
-    const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.IPT) * kSlabK * 2;
-    const uint32_t tx_bytes = 2 * a_box_bytes + 2 * kBBytes;
-
     if (warp == 0) {
         if (lane == 0) {  // ---------------- TMA producer
-            for (int s = 0; s < nslabs; ++s) {
-                const int stage = s % STAGES, it = s / STAGES;
-                if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
-                uint8_t *sb = smem + stage * kStageBytes;
-                mbar_expect_tx(&full[stage], tx_bytes);
-                const int tap = s / cpt, c0 = (s - tap * cpt) * kSlabK;
-                const int kh = tap / 3, kw = tap - kh * 3;
-                tma_load_4d(&tmAh, &full[stage], sb, c0, w0 + kw - 1, h0 + kh - 1, n0);
-                tma_load_4d(&tmAl, &full[stage], sb + kABytes, c0, w0 + kw - 1, h0 + kh - 1, n0);
-                tma_load_2d(&tmBh, &full[stage], sb + 2 * kABytes, tap * p.Cin + c0, nt * BN);
-                tma_load_2d(&tmBl, &full[stage], sb + 2 * kABytes + kBBytes, tap * p.Cin + c0, nt * BN);
+            const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.IPT) * kSlabK * 2;
+            const uint32_t tx_bytes = 2 * a_box_bytes + 2 * kBBytes;
+            uint32_t g = 0;  // slabs issued so far (ring position), continues across tiles
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile / p.mtiles, mt = tile - nt * p.mtiles;
+                const int grp = mt / tiles_per_group, rem = mt - grp * tiles_per_group;
+                const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+                const int n0 = grp * p.IPT, h0 = th * p.BH, w0 = tw * p.BW;
+                for (int s = 0; s < nslabs; ++s, ++g) {
+                    const uint32_t stage = g % STAGES, it = g / STAGES;
+                    mbar_wait(&empty[stage], (it & 1) ^ 1);  // passes at once on the first lap
+                    uint8_t *sb = smem + stage * kStageBytes;
+                    mbar_expect_tx(&full[stage], tx_bytes);
+                    const int tap = s / cpt, c0 = (s - tap * cpt) * kSlabK;
+                    const int kh = tap / 3, kw = tap - kh * 3;
+                    tma_load_4d(&tmAh, &full[stage], sb, c0, w0 + kw - 1, h0 + kh - 1, n0);
+                    tma_load_4d(&tmAl, &full[stage], sb + kABytes, c0, w0 + kw - 1, h0 + kh - 1, n0);
+                    tma_load_2d(&tmBh, &full[stage], sb + 2 * kABytes, tap * p.Cin + c0, nt * BN);
+                    tma_load_2d(&tmBl, &full[stage], sb + 2 * kABytes + kBBytes, tap * p.Cin + c0, nt * BN);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ---------------- MMA issuer
             constexpr uint32_t idesc = make_idesc(kTileM, BN);
-            for (int s = 0; s < nslabs; ++s) {
-                const int stage = s % STAGES, it = s / STAGES;
-                mbar_wait(&full[stage], it & 1);
-                tc_fence_after();
-                const uint32_t sb = smem_u32(smem + stage * kStageBytes);
-                const uint64_t a_hi = make_sdesc(sb), a_lo = make_sdesc(sb + kABytes);
-                const uint64_t b_hi = make_sdesc(sb + 2 * kABytes), b_lo = make_sdesc(sb + 2 * kABytes + kBBytes);
+            uint32_t g = 0, c = 0;  // slab / chunk counters (ring positions)
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int s0 = 0; s0 < nslabs; s0 += p.chunk_slabs, ++c) {
+                    const uint32_t a = c % kAccStages;
+                    mbar_wait(&acc_empty[a], ((c / kAccStages) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + a * BN;
+                    const int s1 = min(s0 + p.chunk_slabs, nslabs);
+                    for (int s = s0; s < s1; ++s, ++g) {
+                        const uint32_t stage = g % STAGES, it = g / STAGES;
+                        mbar_wait(&full[stage], it & 1);
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(smem + stage * kStageBytes);
+                        const uint64_t a_hi = make_sdesc(sb), a_lo = make_sdesc(sb + kABytes);
+                        const uint64_t b_hi = make_sdesc(sb + 2 * kABytes), b_lo = make_sdesc(sb + 2 * kABytes + kBBytes);
+                        // small terms first: they meet the accumulator while it is small
 #pragma unroll
-                for (int k = 0; k < kSlabK / 16; ++k)  // +32 B per K step of 16 inside the swizzle atom
-                    umma_f16(tmem_base + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kSlabK / 16; ++k)  // +32 B per K step of 16 inside the swizzle atom
+                            umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, idesc, (s > s0 || k > 0) ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < kSlabK / 16; ++k) umma_f16(tmem_base + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                        for (int k = 0; k < kSlabK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
-                for (int k = 0; k < kSlabK / 16; ++k)
-                    umma_f16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
-                umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+                        for (int k = 0; k < kSlabK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                        umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+                    }
+                    umma_commit(&acc_full[a]);  // chunk complete -> epilogue may drain it
+                }
             }
-            umma_commit(tmem_full);
         }
-    } else {  // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const int q = warp & 3;
+    } else {  // ---------------- epilogue warps 2..9
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;     // column half
         const int m = q * 32 + lane;
         const int per_img = p.BW * p.BH;
         const int img = m / per_img;
         const int r = m - img * per_img;
         const int rr = r / p.BW, cc = r - rr * p.BW;
-        const bool valid = img < p.IPT && (n0 + img) < p.N && (h0 + rr) < p.H && (w0 + cc) < p.W;
-        const int64_t pix = (((int64_t)(n0 + img) * p.H + (h0 + rr)) * p.W + (w0 + cc));
-        const int64_t obase = pix * p.Cout + (int64_t)nt * BN;
-        const float *bias = p.bias + nt * BN;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t v[32], u[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c), u);
-            tmem_ld_wait();
-            float y[32];
+        uint32_t c = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            float acc[kCols];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float acc = __uint_as_float(v[j]) + __uint_as_float(u[j]);
-                y[j] = fmaxf(fmaf(acc, p.unscale, __ldg(bias + c + j)), 0.0f) * p.out_scale;
+            for (int j = 0; j < kCols; ++j) acc[j] = 0.0f;
+            for (int ch = 0; ch < nchunks; ++ch, ++c) {
+                const uint32_t a = c % kAccStages;
+                mbar_wait(&acc_full[a], (c / kAccStages) & 1);
+                tc_fence_after();
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + half * kCols;
+#pragma unroll
+                for (int j0 = 0; j0 < kCols; j0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(t0 + j0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j0 + j] = __fadd_rn(acc[j0 + j], __uint_as_float(v[j]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[a]);
             }
+            // final epilogue of this tile
+            const int nt = tile / p.mtiles, mt = tile - nt * p.mtiles;
+            const int grp = mt / tiles_per_group, rem = mt - grp * tiles_per_group;
+            const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+            const int n0 = grp * p.IPT, h0 = th * p.BH, w0 = tw * p.BW;
+            const bool valid = img < p.IPT && (n0 + img) < p.N && (h0 + rr) < p.H && (w0 + cc) < p.W;
             if (valid) {
-                if (p.out_f32 != nullptr) {
-                    float4 *dst = reinterpret_cast<float4 *>(p.out_f32 + obase + c);
+                const int64_t pix = (((int64_t)(n0 + img) * p.H + (h0 + rr)) * p.W + (w0 + cc));
+                const int cbase = nt * BN + half * kCols;
+                const int64_t obase = pix * p.Cout + cbase;
+                const float *bias = p.bias + cbase;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-                } else {
-                    uint32_t hi[16], lo[16];
+                for (int j0 = 0; j0 < kCols; j0 += 8) {
+                    float y[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const __half h0v = __float2half_rn(y[2 * j]), h1v = __float2half_rn(y[2 * j + 1]);
-                        const __half l0v = __float2half_rn(y[2 * j] - __half2float(h0v));
-                        const __half l1v = __float2half_rn(y[2 * j + 1] - __half2float(h1v));
-                        hi[j] = (uint32_t)__half_as_ushort(h0v) | ((uint32_t)__half_as_ushort(h1v) << 16);
-                        lo[j] = (uint32_t)__half_as_ushort(l0v) | ((uint32_t)__half_as_ushort(l1v) << 16);
-                    }
-                    uint4 *dh = reinterpret_cast<uint4 *>(p.out_hi + obase + c);
-                    uint4 *dl = reinterpret_cast<uint4 *>(p.out_lo + obase + c);
+                    for (int j = 0; j < 8; ++j)
+                        y[j] = fmaxf(fmaf(acc[j0 + j], p.unscale, __ldg(bias + j0 + j)), 0.0f) * p.out_scale;
+                    if (p.out_f32 != nullptr) {
+                        float4 *dst = reinterpret_cast<float4 *>(p.out_f32 + obase + j0);
+                        dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+                        dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+                    } else {
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) {
+                            const __half h0v = __float2half_rn(y[2 * j]), h1v = __float2half_rn(y[2 * j + 1]);
+                            const __half l0v = __float2half_rn(y[2 * j] - __half2float(h0v));
+                            const __half l1v = __float2half_rn(y[2 * j + 1] - __half2float(h1v));
+                            hi[j] = (uint32_t)__half_as_ushort(h0v) | ((uint32_t)__half_as_ushort(h1v) << 16);
+                            lo[j] = (uint32_t)__half_as_ushort(l0v) | ((uint32_t)__half_as_ushort(l1v) << 16);
+                        }
+                        *reinterpret_cast<uint4 *>(p.out_hi + obase + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(p.out_lo + obase + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
             }
@@ -283,7 +341,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+    if (warp == 1) tmem_dealloc(tmem_base, kAccStages * BN);
 }
 
 // ------------------------------------------------------------ SIMT helpers of the fp16x3 path
@@ -422,9 +480,19 @@ int make_w_map(CUtensorMap *m, const void *base, int Cout, int K, int BN) {
     return 0;
 }
 
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <int BN, int STAGES>
 int launch_conv_tc_t(cudaStream_t st, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh,
-                     const CUtensorMap &bl, const ConvTcParams &p, int mtiles) {
+                     const CUtensorMap &bl, const ConvTcParams &p) {
     constexpr int smem = STAGES * (2 * kABytes + 2 * BN * kSlabK * 2) + 1024 + 256;
     static bool configured = false;
     if (!configured) {
@@ -432,8 +500,9 @@ int launch_conv_tc_t(cudaStream_t st, const CUtensorMap &ah, const CUtensorMap &
         if (e != cudaSuccess) return tc_fail("cudaFuncSetAttribute", cudaGetErrorString(e));
         configured = true;
     }
-    dim3 grid(mtiles, p.Cout / BN);
-    conv3x3_tc_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ah, al, bh, bl, p);
+    const int total = p.mtiles * p.ntiles;
+    const int grid = total < num_sms() ? total : num_sms();  // persistent: one CTA per SM
+    conv3x3_tc_kernel<BN, STAGES><<<grid, kConvThreads, smem, st>>>(ah, al, bh, bl, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tc_fail("conv3x3_tc_kernel launch", cudaGetErrorString(e));
     return 0;
@@ -448,6 +517,16 @@ int ws_ensure(TcWorkspace &ws, int i, size_t bytes) {
     if (e != cudaSuccess) return tc_fail("cudaMalloc(workspace)", cudaGetErrorString(e));
     ws.cap[i] = bytes;
     return 0;
+}
+
+// K-slabs (of 64) accumulated in TMEM between fp32 drains; STITO_TC_CHUNK overrides (developer knob)
+int chunk_slabs() {
+    static int v = 0;
+    if (v == 0) {
+        v = 4;
+        if (const char *e = getenv("STITO_TC_CHUNK")) { const int t = atoi(e); if (t > 0) v = t; }
+    }
+    return v;
 }
 
 inline int blocks_for(int64_t total, int threads) {
@@ -525,8 +604,10 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, con
     p.tilesW = (W + p.BW - 1) / p.BW;
     p.tilesH = (H + p.BH - 1) / p.BH;
     const int groups = (N + p.IPT - 1) / p.IPT;
-    const int mtiles = groups * p.tilesW * p.tilesH;
     const int BN = l.cout >= 256 ? 256 : l.cout;
+    p.mtiles = groups * p.tilesW * p.tilesH;
+    p.ntiles = l.cout / BN;
+    p.chunk_slabs = chunk_slabs();
     if (l.cin % kSlabK != 0 || l.cout % BN != 0 || (BN != 64 && BN != 128 && BN != 256))
         return tc_fail("conv_tc", "unsupported channel counts");
     CUtensorMap ah, al, bh_, bl;
@@ -535,9 +616,9 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, con
     if (make_w_map(&bh_, l.w_hi, l.cout, 9 * l.cin, BN)) return -1;
     if (make_w_map(&bl, l.w_lo, l.cout, 9 * l.cin, BN)) return -1;
     int rc;
-    if (BN == 64) rc = launch_conv_tc_t<64, 4>(st, ah, al, bh_, bl, p, mtiles);
-    else if (BN == 128) rc = launch_conv_tc_t<128, 3>(st, ah, al, bh_, bl, p, mtiles);
-    else rc = launch_conv_tc_t<256, 2>(st, ah, al, bh_, bl, p, mtiles);
+    if (BN == 64) rc = launch_conv_tc_t<64, 4>(st, ah, al, bh_, bl, p);
+    else if (BN == 128) rc = launch_conv_tc_t<128, 3>(st, ah, al, bh_, bl, p);
+    else rc = launch_conv_tc_t<256, 2>(st, ah, al, bh_, bl, p);
     if (rc == 0) *launches += 1;
     return rc;
 }
