@@ -10,9 +10,10 @@
 //   compressor  the ballistics filter is a data-dependent (non-linear) recurrence: 64-sample chunks run
 //               in parallel from guessed states and a Newton / policy iteration (one affine scan over the
 //               chunk boundaries per step) makes the guesses consistent in a handful of passes.
-//   Freeverb    delay lines live in shared memory (one CTA per candidate); comb feedback has a lag
-//               >= 1214 samples and all-pass >= 244, so blocks of 224 samples are time-parallel; the
-//               only lag-1 recurrence (the comb damping one-pole) is a 32-lane affine scan.
+//   Freeverb    delay lines live in shared memory; comb feedback has a lag >= 1214 samples and all-pass
+//               >= 244, so super-steps of 1120 samples (combs) / sub-blocks of 224 (all-passes) are
+//               time-parallel; the only lag-1 recurrence (the comb damping one-pole) is a 32-lane affine
+//               scan.  Comb warps and all-pass warps of a CTA run concurrently (see reverb_core_kernel).
 //   delay       lag-d feedback: the d residue classes are independent serial chains.
 // All float arithmetic uses explicit _rn intrinsics where the oracle (compiled with
 // -ffp-contract=off) rounds each operation separately.
@@ -516,14 +517,25 @@ __global__ void __launch_bounds__(NCH * 256) reverb_kernel(SigView in, const flo
 // ---------------------------------------------------------------- reverb, fast path
 // The two channels of juce::Reverb share only the mono input sum and the final wet cross-mix, so the
 // comb/all-pass network of every (candidate, channel) runs in its own CTA and a trivial element-wise
-// kernel does the mix.  Delay lines are power-of-two rings (combs 2048, all-passes 1024 floats) indexed
-// with (n - delay) & mask: no per-ring position state and no wrap-around branches.  Same block scheme as
-// reverb_kernel: blocks of kRevFastBlock samples, phase 1 = comb outputs (delayed, independent of the
-// block) + sample-parallel all-passes, phase 2 = one warp per comb updates its ring (affine scan of the
-// damping one-pole across the 32 lanes).
-constexpr int kRevFastSeg = 7;
-constexpr int kRevFastBlock = 32 * kRevFastSeg;  // 224 <= shortest all-pass line at 44.1/48 kHz
-constexpr int kCombRing = 2048, kApRing = 1024;
+// kernel does the mix.  Delay lines are power-of-two rings (combs 4096, all-passes 1024 floats) indexed
+// with (n - delay) & mask: no per-ring position state and no wrap-around branches.
+//
+// Time is cut into super-steps of S = 32*seg samples, S <= shortest comb delay, so that inside a
+// super-step every delayed read refers to samples of EARLIER super-steps:
+//   * 8 comb warps (one comb each): lane l owns `seg` consecutive samples; the only lag-1 recurrence (the
+//     damping one-pole) is a zero-state pass + 32-lane affine scan + replay, all in registers;
+//   * 7 all-pass warps (224 threads = one sub-block <= shortest all-pass delay): sum the 8 comb outputs
+//     (= ring values of earlier super-steps, read straight from the comb rings) and run the 4 series
+//     all-passes sample-parallel, sub-block after sub-block, synchronised by a named barrier of their own.
+// The two groups do not depend on each other inside a super-step (the 4096-float comb rings keep a full
+// super-step of history beyond the longest delay, so the comb writes cannot clobber what the all-pass group
+// still has to read) and run concurrently; one __syncthreads per super-step (429 for 10 s) is the only
+// CTA-wide barrier.  The next super-step's input is prefetched into a double buffer meanwhile.
+constexpr int kRevMaxSegF = 35;          // instantiated for seg = 35 (>= 44.3 kHz: S = 1120 = 5 sub-blocks) and 32
+constexpr int kRevSub = 224;             // all-pass sub-block: <= shortest all-pass line at >= 44.1 kHz
+constexpr int kCombRing = 4096, kApRing = 1024;
+constexpr int kRevCombThreads = 256, kRevThreads = kRevCombThreads + kRevSub;
+constexpr int kRevMaxS = 32 * kRevMaxSegF;
 
 struct ReverbFastGeom {
     int comb_delay[2][8];
@@ -531,37 +543,27 @@ struct ReverbFastGeom {
 };
 
 // inst = (p, c): stereo != 0 -> input (l + r) * 0.015, tunings of channel c; else input x_c * 0.015, left tunings
-__global__ void __launch_bounds__(256) reverb_core_kernel(SigView in, const float *in_peak, float *wet, int chs,
-                                                          int stereo, int64_t L, ReverbFastGeom g,
-                                                          const ReverbParams *prm) {
+template <int SEG>
+__global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in, const float *in_peak, float *wet,
+                                                                     int chs, int stereo, int64_t L,
+                                                                     ReverbFastGeom g, const ReverbParams *prm) {
     extern __shared__ float sm[];
     float *comb = sm;                        // [8][kCombRing]
     float *ap = sm + 8 * kCombRing;          // [4][kApRing]
-    float *mixin = ap + 4 * kApRing;         // [kRevFastBlock]
+    float *inbuf = ap + 4 * kApRing;         // [2][kRevMaxS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int inst = blockIdx.x;
     const int p = inst / chs, c = inst - p * chs;
     const int tune = stereo ? c : 0;
-    for (int i = tid; i < 8 * kCombRing + 4 * kApRing; i += blockDim.x) sm[i] = 0.0f;
+    for (int i = tid; i < 8 * kCombRing + 4 * kApRing; i += kRevThreads) sm[i] = 0.0f;
     const ReverbParams q = prm[p];
     const bool has_div = in_peak != nullptr;
     const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
-    const float keep = __fsub_rn(1.0f, q.damp);
-    int cd[8], ad[4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cd[j] = g.comb_delay[tune][j];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ad[j] = g.ap_delay[tune][j];
-    const int my_delay = g.comb_delay[tune][warp];  // phase 2: warp w owns comb w
-    float *my_ring = comb + warp * kCombRing;
-    float fstore = 0.0f, dpow = 1.0f;
-#pragma unroll
-    for (int i = 0; i < kRevFastSeg; ++i) dpow = __fmul_rn(dpow, q.damp);
+    constexpr int seg = SEG, S = 32 * SEG;
+    constexpr int nsub = (S + kRevSub - 1) / kRevSub;
 
-    const bool p1 = tid < kRevFastBlock;
-    float *dst = wet + (int64_t)inst * L;
     auto fetch = [&](int64_t n) -> float {
-        if (!p1 || n >= L) return 0.0f;
+        if (n >= L) return 0.0f;
         if (stereo) {
             float l = load_in(in, p, 0, n), r = load_in(in, p, 1, n);
             if (has_div) { l = l / div; r = r / div; }
@@ -571,43 +573,51 @@ __global__ void __launch_bounds__(256) reverb_core_kernel(SigView in, const floa
         if (has_div) x = x / div;
         return __fmul_rn(x, 0.015f);
     };
-    float in0 = fetch(tid), in1 = fetch((int64_t)kRevFastBlock + tid);  // two blocks of prefetch
+    for (int i = tid; i < S; i += kRevThreads) inbuf[i] = fetch(i);
     __syncthreads();
 
-    for (int64_t n0 = 0; n0 < L; n0 += kRevFastBlock) {
-        const int nb = (int)min((int64_t)kRevFastBlock, L - n0);
+    const bool comb_role = tid < kRevCombThreads;
+    // comb role state
+    const int my_delay = g.comb_delay[tune][warp & 7];
+    float *my_ring = comb + (warp & 7) * kCombRing;
+    const float keep = __fsub_rn(1.0f, q.damp);
+    float fstore = 0.0f, dpow = 1.0f;
+#pragma unroll
+    for (int i = 0; i < SEG; ++i) dpow = __fmul_rn(dpow, q.damp);
+    // all-pass role state
+    const int a = tid - kRevCombThreads;
+    int cd[8], ad[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cd[j] = g.comb_delay[tune][j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ad[j] = g.ap_delay[tune][j];
+    float *dst = wet + (int64_t)inst * L;
+
+    int buf = 0;
+    for (int64_t n0 = 0; n0 < L; n0 += S, buf ^= 1) {
         const int nbase = (int)(n0 & (kCombRing * kApRing - 1));  // only the low bits matter for the masks
-        if (p1) {
-            const float inp = in0;
-            in0 = in1;
-            in1 = fetch(n0 + 2 * kRevFastBlock + tid);
-            const int n = nbase + tid;
-            mixin[tid] = inp;
-            float v = 0.0f;
+        // prefetch the next super-step's input into registers now (the loads fly while this super-step is
+        // computed); it is parked in the other half of the double buffer just before the barrier below
+        constexpr int kPre = (kRevMaxS + kRevThreads - 1) / kRevThreads;
+        float pre_l[kPre], pre_r[kPre];  // raw samples: no arithmetic before the end of the super-step
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v = __fadd_rn(v, comb[j * kCombRing + ((n - cd[j]) & (kCombRing - 1))]);
-            const bool act = tid < nb;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                float *slot_r = ap + s * kApRing + ((n - ad[s]) & (kApRing - 1));
-                const float bv = *slot_r;
-                const float t = undenorm(__fadd_rn(v, __fmul_rn(bv, 0.5f)));
-                if (act) ap[s * kApRing + (n & (kApRing - 1))] = t;
-                v = __fsub_rn(bv, v);
-            }
-            if (act) dst[n0 + tid] = v;
+        for (int k = 0; k < kPre; ++k) {
+            const int64_t n = n0 + S + tid + k * kRevThreads;
+            const bool ok = (tid + k * kRevThreads) < S && n < L;
+            pre_l[k] = ok ? load_in(in, p, stereo ? 0 : c, n) : 0.0f;
+            pre_r[k] = (ok && stereo) ? load_in(in, p, 1, n) : 0.0f;
         }
-        __syncthreads();
-        {   // phase 2: warp -> comb
-            const int i0 = lane * kRevFastSeg;
+        if (comb_role) {
+            const float *inb = inbuf + buf * kRevMaxS;
+            const int i0 = lane * seg;
             const int n = nbase + i0;
-            float o[kRevFastSeg];
+            float o[SEG];
 #pragma unroll
-            for (int i = 0; i < kRevFastSeg; ++i) o[i] = my_ring[(n + i - my_delay) & (kCombRing - 1)];
-            float z = 0.0f;
+            for (int i = 0; i < SEG; ++i) o[i] = my_ring[(n + i - my_delay) & (kCombRing - 1)];
+            float z = 0.0f;  // zero-state response of the damping one-pole over my segment
 #pragma unroll
-            for (int i = 0; i < kRevFastSeg; ++i) z = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(z, q.damp)));
-            float A = dpow, Bv = z;
+            for (int i = 0; i < SEG; ++i) z = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(z, q.damp)));
+            float A = dpow, Bv = z;  // affine map of my segment: s -> A*s + Bv; inclusive scan
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const float Ap = __shfl_up_sync(0xffffffffu, A, d);
@@ -615,15 +625,44 @@ __global__ void __launch_bounds__(256) reverb_core_kernel(SigView in, const floa
                 if (lane >= d) { Bv = fmaf(Bp, A, Bv); A = A * Ap; }
             }
             const float s_out = fmaf(A, fstore, Bv);
-            float s = __shfl_up_sync(0xffffffffu, s_out, 1);
-            if (lane == 0) s = fstore;
+            float sv = __shfl_up_sync(0xffffffffu, s_out, 1);
+            if (lane == 0) sv = fstore;
 #pragma unroll
-            for (int i = 0; i < kRevFastSeg; ++i) {
-                s = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(s, q.damp)));
-                const float t = undenorm(__fadd_rn(mixin[i0 + i], __fmul_rn(s, q.fb)));
-                if (i0 + i < nb) my_ring[(n + i) & (kCombRing - 1)] = t;
+            for (int i = 0; i < SEG; ++i) {
+                sv = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(sv, q.damp)));
+                const float tv = undenorm(__fadd_rn(inb[i0 + i], __fmul_rn(sv, q.fb)));
+                my_ring[(n + i) & (kCombRing - 1)] = tv;
             }
-            fstore = __shfl_sync(0xffffffffu, s, 31);
+            fstore = __shfl_sync(0xffffffffu, sv, 31);
+        } else {
+            for (int sb = 0; sb < nsub; ++sb) {
+                const int off = sb * kRevSub + a;
+                if (off < S) {
+                    const int n = nbase + off;
+                    float v = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v = __fadd_rn(v, comb[j * kCombRing + ((n - cd[j]) & (kCombRing - 1))]);
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const float bv = ap[s * kApRing + ((n - ad[s]) & (kApRing - 1))];
+                        const float tv = undenorm(__fadd_rn(v, __fmul_rn(bv, 0.5f)));
+                        ap[s * kApRing + (n & (kApRing - 1))] = tv;
+                        v = __fsub_rn(bv, v);
+                    }
+                    if (n0 + off < L) dst[n0 + off] = v;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kRevSub) : "memory");  // all-pass group only
+            }
+        }
+        {
+            float *nxt = inbuf + (buf ^ 1) * kRevMaxS;
+#pragma unroll
+            for (int k = 0; k < kPre; ++k) {
+                const int i = tid + k * kRevThreads;
+                float l = pre_l[k], r = pre_r[k];
+                if (has_div) { l = l / div; r = r / div; }
+                if (i < S) nxt[i] = __fmul_rn(stereo ? __fadd_rn(l, r) : l, 0.015f);
+            }
         }
         __syncthreads();
     }
@@ -783,16 +822,22 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
             min_ap = g.ap_size[c][j] < min_ap ? g.ap_size[c][j] : min_ap;
         }
     }
-    if (wet_scratch != nullptr && max_comb <= kCombRing && max_ap <= kApRing && min_ap >= kRevFastBlock) {
+    int min_comb = 1 << 30;
+    for (int c = 0; c < 2; ++c)
+        for (int j = 0; j < 8; ++j) min_comb = g.comb_size[c][j] < min_comb ? g.comb_size[c][j] : min_comb;
+    const int seg = min_comb >= 32 * kRevMaxSegF ? kRevMaxSegF : 32;
+    if (wet_scratch != nullptr && min_comb >= 32 * seg && max_comb + 32 * seg <= kCombRing &&
+        max_ap + kRevSub <= kApRing && min_ap >= kRevSub) {
         ReverbFastGeom fg;
         for (int c = 0; c < 2; ++c) {
             for (int j = 0; j < 8; ++j) fg.comb_delay[c][j] = g.comb_size[c][j];
             for (int j = 0; j < 4; ++j) fg.ap_delay[c][j] = g.ap_size[c][j];
         }
-        const size_t smem = (size_t)(8 * kCombRing + 4 * kApRing + kRevFastBlock) * sizeof(float);
-        e = cudaFuncSetAttribute(reverb_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const size_t smem = (size_t)(8 * kCombRing + 4 * kApRing + 2 * kRevMaxS) * sizeof(float);
+        auto kern = seg == kRevMaxSegF ? reverb_core_kernel<kRevMaxSegF> : reverb_core_kernel<32>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        reverb_core_kernel<<<P * chs, 256, smem, st>>>(in, in_peak, wet_scratch, chs, stereo, L, fg, prm);
+        kern<<<P * chs, kRevThreads, smem, st>>>(in, in_peak, wet_scratch, chs, stereo, L, fg, prm);
         dim3 grid(grid_for(L, 256, P * chs), P * chs);
         reverb_mix_kernel<<<grid, 256, 0, st>>>(in, in_peak, wet_scratch, out, chs, stereo, L, prm, out_peak);
         *launches += 2;
