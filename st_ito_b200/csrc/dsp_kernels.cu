@@ -226,19 +226,41 @@ __global__ void __launch_bounds__(kCsT, 1) compressor_scan_kernel(SigView in, co
     float pk = 0.0f;
     if (t == 0) *carry_s = 0.0f;
 
+    // The next super-block is prefetched into registers (16 x 16 B per thread = the whole 128 KB super-block
+    // in flight at once) while the current one is iterated on; float4 loads when the stream is 16-byte aligned.
+    constexpr int kPre = kCsSB / 4 / kCsT;  // 16
+    float4 pre[kPre];
+    const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    auto issue_loads = [&](int64_t b) {
+        const int n = (int)max((int64_t)0, min((int64_t)kCsSB, L - b));
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int i4 = 4 * (t + k * kCsT);
+            if (aligned && i4 + 3 < n) {
+                pre[k] = __ldg(reinterpret_cast<const float4 *>(src + b + i4));
+            } else {
+                pre[k].x = i4 + 0 < n ? __ldg(src + b + i4 + 0) : 0.0f;
+                pre[k].y = i4 + 1 < n ? __ldg(src + b + i4 + 1) : 0.0f;
+                pre[k].z = i4 + 2 < n ? __ldg(src + b + i4 + 2) : 0.0f;
+                pre[k].w = i4 + 3 < n ? __ldg(src + b + i4 + 3) : 0.0f;
+            }
+        }
+    };
+    issue_loads(0);
+
     for (int64_t b0 = 0; b0 < L; b0 += kCsSB) {
         const int nb = (int)min((int64_t)kCsSB, L - b0);
-        // coalesced load, transposed into chunk rows
-#pragma unroll 8
-        for (int idx = t; idx < kCsSB; idx += kCsT) {
-            float v = 0.0f;
-            if (idx < nb) {
-                v = __ldg(src + b0 + idx);
-                if (has_div) v = v / div;
-            }
-            xs[(idx >> 6) * kCsPitch + (idx & 63)] = v;
+        // park the prefetched super-block in shared memory, transposed into chunk rows
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int f = t + k * kCsT;
+            float *d4 = xs + (f >> 4) * kCsPitch + (f & 15) * 4;
+            float4 v = pre[k];
+            if (has_div) { v.x = v.x / div; v.y = v.y / div; v.z = v.z / div; v.w = v.w / div; }
+            d4[0] = v.x; d4[1] = v.y; d4[2] = v.z; d4[3] = v.w;
         }
         __syncthreads();
+        issue_loads(b0 + kCsSB);
         const int len = max(0, min(kCsC, nb - t * kCsC));
         float s_in = *carry_s;
 
@@ -301,8 +323,21 @@ __global__ void __launch_bounds__(kCsT, 1) compressor_scan_kernel(SigView in, co
             if (t == kCsT - 1) *carry_s = env;
         }
         __syncthreads();
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll 4
+            for (int k = 0; k < kPre; ++k) {
+                const int f = t + k * kCsT, i4 = 4 * f;
+                const float *s4 = xs + (f >> 4) * kCsPitch + (f & 15) * 4;
+                if (i4 + 3 < nb) {
+                    *reinterpret_cast<float4 *>(dst + b0 + i4) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+                } else {
+                    for (int e = 0; e < 4; ++e) if (i4 + e < nb) dst[b0 + i4 + e] = s4[e];
+                }
+            }
+        } else {
 #pragma unroll 8
-        for (int idx = t; idx < nb; idx += kCsT) dst[b0 + idx] = xs[(idx >> 6) * kCsPitch + (idx & 63)];
+            for (int idx = t; idx < nb; idx += kCsT) dst[b0 + idx] = xs[(idx >> 6) * kCsPitch + (idx & 63)];
+        }
         __syncthreads();
     }
     if (out_peak != nullptr) {
