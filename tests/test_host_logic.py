@@ -1,0 +1,251 @@
+"""CPU tests (no GPU, no compute calls into libstito): the C-ABI library loads and exports every symbol the
+header declares with matching struct layouts, the host-side chain compilation / CMA-ES / sharding logic, and the
+N > 1 host loop under a world_size-2 gloo group (the CUDA engine is replaced by a deterministic fake)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------- C ABI
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "stito.h")).read()
+    return sorted(set(re.findall(r"STITO_API\s+[\w\s\*]+?\b(stito_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from st_ito_b200 import _lib
+
+    _lib.build()
+    names = _header_functions()
+    assert len(names) >= 15 and "stito_eval_population" in names
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"libstito.so does not export {n}"
+    assert sorted(_lib.EXPORTS) == names, "st_ito_b200/_lib.py binds a different symbol set than include/stito.h"
+    # nothing but the ABI is visible (the kernels are built with -fvisibility=hidden)
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert sorted(e for e in exported if e.startswith("stito_")) == names
+    assert L.stito_version() >= 100
+    L.stito_last_error.restype = ctypes.c_char_p
+    assert isinstance(L.stito_last_error(), bytes)
+
+
+def test_ctypes_struct_layouts_match_the_header():
+    """sizeof/offsetof of the ctypes mirrors against a C program compiled from include/stito.h."""
+    from st_ito_b200 import _lib
+
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "stito.h"
+int main(void) {
+    printf("%zu %zu %zu %zu ", sizeof(stito_fx_desc), sizeof(stito_chain_desc), sizeof(stito_encoder_weights), sizeof(stito_timing));
+    printf("%zu %zu %zu ", offsetof(stito_fx_desc, fixed_raw), offsetof(stito_chain_desc, fx), offsetof(stito_chain_desc, sample_rate));
+    printf("%zu %zu %zu\n", offsetof(stito_encoder_weights, conv_w), offsetof(stito_encoder_weights, mel_w), offsetof(stito_timing, ms_conv));
+    return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "layout.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(d, "layout")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        got = [int(v) for v in subprocess.check_output([exe], text=True).split()]
+    want = [ctypes.sizeof(_lib.FxDesc), ctypes.sizeof(_lib.ChainDesc), ctypes.sizeof(_lib.EncoderWeights),
+            ctypes.sizeof(_lib.Timing), _lib.FxDesc.fixed_raw.offset, _lib.ChainDesc.fx.offset,
+            _lib.ChainDesc.sample_rate.offset, _lib.EncoderWeights.conv_w.offset, _lib.EncoderWeights.mel_w.offset,
+            _lib.Timing.ms_conv.offset]
+    assert got == want
+
+
+def test_product_path_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a box without CUDA the host mirror raises instead of computing elsewhere."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from st_ito_b200 import effects
+    from st_ito_b200.utils import make_synthetic_param_model
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        effects.BasicParametricEQ().process(np.zeros((1, 64), dtype=np.float32), 48000)
+    m = make_synthetic_param_model(seed=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 2, 48000))
+
+
+# -------------------------------------------------------------------------------- chain compilation
+def _chain(kinds=("eq", "comp", "reverb"), fixed=None):
+    from st_ito_b200 import effects
+
+    table = {"eq": ("ParametricEQ", effects.BasicParametricEQ, 1), "comp": ("Compressor", effects.BasicCompressor, 1),
+             "dist": ("Distortion", effects.BasicDistortion, 1), "delay": ("Delay", effects.BasicDelay, 2),
+             "reverb": ("Reverb", effects.BasicReverb, 2)}
+    plugins = {}
+    for k in kinds:
+        name, cls, ch = table[k]
+        plugins[name] = {"class_path": cls, "num_params": None, "num_channels": ch,
+                         "fixed_parameters": dict((fixed or {}).get(k, {}))}
+    return plugins
+
+
+def test_load_plugins_and_compile_chain_index_bookkeeping(capsys):
+    from st_ito_b200 import _lib
+    from st_ito_b200.engine import compile_chain
+    from st_ito_b200.style_transfer import load_plugins, parameters_to_dict
+
+    plugins, D, init = load_plugins(_chain(fixed={"comp": {"ratio": 4.0}}))
+    capsys.readouterr()
+    assert D == 29 == len(init)  # (1+18) + (1+4) + (1+4): one dead our_bypass slot per plugin
+    assert [p["parameter_names"][0] for p in plugins.values()] == ["our_bypass"] * 3
+    desc, Dc = compile_chain(plugins, 48000)
+    assert Dc == D and desc.num_fx == 3 and desc.num_w == 29
+    eq, comp, rev = desc.fx[0], desc.fx[1], desc.fx[2]
+    assert (eq.kind, comp.kind, rev.kind) == (_lib.FX_EQ, _lib.FX_COMPRESSOR, _lib.FX_REVERB)
+    assert list(eq.w_index[:18]) == list(range(1, 19))  # slot 0 is our_bypass
+    # the fixed ratio still consumes its w slot (style_transfer.py:80-85) but maps to the fixed raw value
+    assert list(comp.w_index[:4]) == [20, -1, 22, 23]
+    assert comp.fixed_raw[1] == pytest.approx((4.0 - 1.0) / 19.0)
+    assert list(rev.w_index[:4]) == [25, 26, 27, 28]
+    w = np.linspace(0, 1, D)
+    d = parameters_to_dict(w, plugins)
+    assert d["Compressor"]["ratio"] == pytest.approx(4.0) and d["ParametricEQ"]["our_bypass"] == w[0]
+    assert d["Reverb"]["width"] == pytest.approx(w[28])
+    with pytest.raises(AssertionError):  # Parameter.set_value range check (effects.py:792)
+        compile_chain(load_plugins(_chain(fixed={"comp": {"ratio": 99.0}}))[0], 48000)
+    with pytest.raises(ValueError, match="vst_filepath"):
+        load_plugins({"x": {"num_channels": 1}})
+
+
+def test_run_optim_style_loader_has_no_bypass_slots():
+    """scripts/run_optim.py:410-437 records parameter_names without our_bypass: D = 18 for the EQ."""
+    from st_ito_b200.engine import compile_chain
+
+    plugins = _chain(("eq",))
+    inst = plugins["ParametricEQ"]["class_path"]()
+    plugins["ParametricEQ"].update(instance=inst, parameter_names=list(inst.parameters), num_params=18)
+    desc, D = compile_chain(plugins, 48000)
+    assert D == 18 and list(desc.fx[0].w_index[:18]) == list(range(18))
+
+
+# -------------------------------------------------------------------------------------------- CMA
+def test_cma_minimises_inside_the_box_and_is_seed_reproducible():
+    from st_ito_b200 import cma
+
+    target = np.linspace(0.1, 0.9, 12)
+
+    def f(x):
+        return float(np.sum((np.asarray(x) - target) ** 2))
+
+    runs = []
+    for _ in range(2):
+        es = cma.CMAEvolutionStrategy(np.full(12, 0.5), 0.33, {"bounds": [0, 1], "popsize": 16, "seed": 5,
+                                                               "verbose": -9})
+        assert es.result[0] is None
+        for _ in range(120):
+            X = es.ask()
+            assert len(X) == 16 and all(np.all((x >= 0) & (x <= 1)) for x in X)
+            es.tell(X, [f(x) for x in X])
+        runs.append((es.result[0].copy(), es.result[1]))
+    assert runs[0][1] < 1e-6 and np.allclose(runs[0][0], target, atol=2e-3)
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]
+
+
+def test_shard_bounds_cover_the_population_once():
+    from st_ito_b200.dist import shard_bounds
+
+    for P, G in [(64, 8), (64, 1), (10, 4), (3, 8), (256, 8), (1, 2)]:
+        seen = []
+        for r in range(G):
+            lo, hi, chunk = shard_bounds(P, G, r)
+            assert 0 <= lo <= hi <= P and hi - lo <= chunk
+            seen += list(range(lo, hi))
+        assert seen == list(range(P))
+
+
+# ------------------------------------------------------------------------------ world_size 2, gloo
+_WORKER = r'''
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+rank = int(sys.argv[1]); world = int(sys.argv[2]); port = sys.argv[3]; out = sys.argv[4]
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=port, RANK=str(rank), WORLD_SIZE=str(world))
+if world > 1:
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+from st_ito_b200 import dist as sdist, effects, style_transfer
+from st_ito_b200.utils import get_param_embeds, make_synthetic_param_model
+
+# helpers first
+rows = torch.arange(5 * 3, dtype=torch.float32).reshape(5, 3)
+lo, hi, _ = sdist.shard_bounds(5, world, rank)
+g = sdist.all_gather_rows(rows[lo:hi], 5)
+assert torch.equal(g, rows), g
+b = sdist.broadcast_array(np.full(4, float(rank + 1)))
+assert np.all(b == 1.0)
+
+class FakeEngine:  # stands in for the libstito handle: fitness = distance of w to a hidden optimum
+    calls = []
+    def set_chain(self, d): pass
+    def set_target_embeds(self, m, s): pass
+    def set_input(self, x, min_len=0): return max(x.shape[-1], min_len)
+    def eval_population(self, W, start, length, want_embeds=False, want_audio=False, in_chs=None):
+        W = np.asarray(W); FakeEngine.calls.append((W.shape[0], start, length))
+        wstar = np.linspace(0.2, 0.8, W.shape[1]) if W.shape[0] else None
+        fit = torch.tensor([float(np.sum((w - wstar) ** 2)) - 1.0 for w in W], dtype=torch.float32)
+        return fit, None, None
+
+model = make_synthetic_param_model(seed=1)
+model.stito_engine = lambda *a, **k: FakeEngine()
+model.forward = lambda x: (torch.ones(x.shape[0], 512), torch.ones(x.shape[0], 512))
+style_transfer.process_audio = lambda x, w, sr, plugins, normalize_stages=False: np.asarray(x, dtype=np.float32)
+import contextlib, io
+with contextlib.redirect_stdout(io.StringIO()):
+    plugins, D, _ = style_transfer.load_plugins(effects.make_chain("eq"))
+x = torch.randn(1, 1, 300000, generator=torch.Generator().manual_seed(0))
+t = torch.randn(1, 1, 300000, generator=torch.Generator().manual_seed(1))
+res = style_transfer.run_es(x, t, 48000, plugins, model, get_param_embeds, max_iters=6, popsize=10, sigma0=0.33,
+                            find_w0=True, seed={seed}, verbose=False)
+json.dump({{"fopt": res["fopt"], "wopt": list(map(float, res["wopt"])), "hist": [float(v) for v in res["fval_history"][1:]],
+           "calls": FakeEngine.calls}}, open(out, "w"))
+if world > 1:
+    dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def _run_world(world, seed, tmp_path, port):
+    script = tmp_path / f"worker_{world}_{seed}.py"
+    script.write_text(_WORKER.format(root=ROOT, seed=seed))
+    outs = [tmp_path / f"out_{world}_{seed}_{r}.json" for r in range(world)]
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world), str(port), str(outs[r])],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    logs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, log in zip(procs, logs):
+        assert p.returncode == 0, log[-3000:]
+    import json
+
+    return [json.load(open(o)) for o in outs]
+
+
+@pytest.mark.parametrize("seed", [0, None])
+def test_run_es_population_sharding_world2_gloo(tmp_path, seed):
+    """Two ranks (gloo, CPU) shard every population, all-gather the fitness and stay in lock step: identical
+    results on both ranks, identical to the single-process run when the CMA-ES is seeded; with seed=None rank 0's
+    population is broadcast instead (style_transfer.replicated)."""
+    port = 29600 + (os.getpid() % 300) + (0 if seed is None else 1)
+    two = _run_world(2, repr(seed), tmp_path, port)
+    assert two[0]["fopt"] == two[1]["fopt"] and two[0]["wopt"] == two[1]["wopt"] and two[0]["hist"] == two[1]["hist"]
+    # every rank evaluated half of each population of 10, on the full-length view (L > 262144, no crop)
+    assert all(c == [5, 0, 300000] for c in two[0]["calls"]) and len(two[0]["calls"]) == 7
+    if seed is not None:
+        one = _run_world(1, repr(seed), tmp_path, port + 2)[0]
+        assert one["fopt"] == two[0]["fopt"] and one["wopt"] == two[0]["wopt"]
+        assert all(c == [10, 0, 300000] for c in one["calls"])
+        assert one["fopt"] <= min(one["hist"]) and one["fopt"] < 0.5  # best-so-far of a distance-to-optimum objective
