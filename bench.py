@@ -111,9 +111,12 @@ def cpu_candidates(x, W, plugins, model, target_embeds):
 
     from oracle import cnn14, dsp
 
-    audios = torch.stack([torch.from_numpy(dsp.process_audio(x, w, SR, plugins)) for w in W])
-    emb = cnn14.get_param_embeds(audios, model, SR)
-    return cnn14.fitness(emb, target_embeds)
+    fits = []
+    for i in range(0, len(W), 8):  # encoder in batches of 8 candidates: bounded activation memory on the host
+        audios = torch.stack([torch.from_numpy(dsp.process_audio(x, w, SR, plugins)) for w in W[i:i + 8]])
+        emb = cnn14.get_param_embeds(audios, model, SR)
+        fits.append(cnn14.fitness(emb, target_embeds))
+    return torch.cat(fits)
 
 
 def cpu_setup(x, chain_kinds):
@@ -138,7 +141,7 @@ def run_reference(args, rank):
 
     x = make_workload(args.seconds)
     plugins, D, model, te = cpu_setup(x, ["eq", "comp", "reverb"])
-    sample = args.cpu_sample
+    sample = args.ref_sample
     times = []
     for step in range(args.warmup + args.steps):
         W = np.random.RandomState(100 + step).rand(sample, D)
@@ -314,7 +317,10 @@ def main():
     ap.add_argument("--pop", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--precision", type=int, default=None, help="0 = fp32 CUDA cores, 1 = fp16x3 tcgen05")
-    ap.add_argument("--cpu-sample", type=int, default=4)
+    ap.add_argument("--cpu-sample", type=int, default=96,
+                    help="candidates timed for cpu_baseline in the default arm (about 10-30 s of host work)")
+    ap.add_argument("--ref-sample", type=int, default=16,
+                    help="candidates per step of the --impl reference arm (bounded sample of the P=64 population)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
