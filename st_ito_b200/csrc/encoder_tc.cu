@@ -152,6 +152,7 @@ struct ConvTcParams {
     int tilesW, tilesH;
     int mtiles, ntiles;       // tile grid; the persistent CTAs walk tile = m + mtiles * n
     int chunk_slabs;          // K-slabs accumulated inside TMEM before the fp32 drain (see below)
+    int pool;                 // 1: fuse the block's 2x2 average pool into the epilogue (output [N][H/2][W/2][Cout])
 };
 
 constexpr int kTileM = 128;
@@ -163,6 +164,67 @@ constexpr int kAccStages = 2;                    // TMEM accumulator ring
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Final epilogue of one tile for one epilogue thread (one output pixel row x kCols channels held in acc):
+// * unscale + bias, ReLU, optional fused 2x2 average pool, fp16 hi/lo split (or fp32) and the NHWC store.
+template <int kCols>
+__device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&acc)[kCols], int tile,
+                                           int tiles_per_group, int img, int rr, int cc, int BN, int col0,
+                                           const float *sbias) {
+    const int nt = tile / p.mtiles, mt = tile - nt * p.mtiles;
+    const int grp = mt / tiles_per_group, rem = mt - grp * tiles_per_group;
+    const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+    const int n0 = grp * p.IPT, h0 = th * p.BH, w0 = tw * p.BW;
+    const int hh = h0 + rr, ww = w0 + cc;
+    const int cbase = nt * BN + col0;
+    const float *bias = sbias + cbase;
+    bool store;
+    int64_t obase;
+    if (p.pool) {
+        // 2x2 average pool (floor): the window (rr, rr+1) x (cc, cc+1) lives in lanes {l, l^1, l^BW, l^BW^1}
+        // of this warp (tile rows are BW <= 16 pixels wide); the lane of the even corner stores.
+        const int Ho = p.H >> 1, Wo = p.W >> 1;
+        store = img < p.IPT && (n0 + img) < p.N && !(rr & 1) && !(cc & 1) && (hh >> 1) < Ho && (ww >> 1) < Wo;
+        obase = (((int64_t)(n0 + img) * Ho + (hh >> 1)) * Wo + (ww >> 1)) * p.Cout + cbase;
+    } else {
+        store = img < p.IPT && (n0 + img) < p.N && hh < p.H && ww < p.W;
+        obase = (((int64_t)(n0 + img) * p.H + hh) * p.W + ww) * p.Cout + cbase;
+    }
+#pragma unroll
+    for (int j0 = 0; j0 < kCols; j0 += 8) {
+        float y[8];
+        const float4 bq0 = *reinterpret_cast<const float4 *>(bias + j0);
+        const float4 bq1 = *reinterpret_cast<const float4 *>(bias + j0 + 4);
+        const float bv[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = fmaxf(fmaf(acc[j0 + j], p.unscale, bv[j]), 0.0f);
+            if (p.pool) {
+                v = v + __shfl_xor_sync(0xffffffffu, v, 1);
+                v = v + __shfl_xor_sync(0xffffffffu, v, p.BW);
+            }
+            y[j] = v * p.out_scale;
+        }
+        if (!store) continue;
+        if (p.out_f32 != nullptr) {
+            float4 *dst = reinterpret_cast<float4 *>(p.out_f32 + obase + j0);
+            dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+            dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+        } else {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __half h0v = __float2half_rn(y[2 * j]), h1v = __float2half_rn(y[2 * j + 1]);
+                const __half l0v = __float2half_rn(y[2 * j] - __half2float(h0v));
+                const __half l1v = __float2half_rn(y[2 * j + 1] - __half2float(h1v));
+                hi[j] = (uint32_t)__half_as_ushort(h0v) | ((uint32_t)__half_as_ushort(h1v) << 16);
+                lo[j] = (uint32_t)__half_as_ushort(l0v) | ((uint32_t)__half_as_ushort(l1v) << 16);
+            }
+            *reinterpret_cast<uint4 *>(p.out_hi + obase + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(p.out_lo + obase + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
 }
 
 // Persistent, warp-specialised implicit-GEMM convolution.
@@ -195,6 +257,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
     uint64_t *acc_full = empty + STAGES;
     uint64_t *acc_empty = acc_full + kAccStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + kAccStages);
+    float *sbias = reinterpret_cast<float *>(smem + STAGES * kStageBytes + 256);  // [Cout] (<= 2048 floats)
+    for (int i = threadIdx.x; i < p.Cout; i += kConvThreads) sbias[i] = __ldg(p.bias + i);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_group = p.tilesW * p.tilesH;
@@ -301,42 +365,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
             }
-            // final epilogue of this tile
-            const int nt = tile / p.mtiles, mt = tile - nt * p.mtiles;
-            const int grp = mt / tiles_per_group, rem = mt - grp * tiles_per_group;
-            const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
-            const int n0 = grp * p.IPT, h0 = th * p.BH, w0 = tw * p.BW;
-            const bool valid = img < p.IPT && (n0 + img) < p.N && (h0 + rr) < p.H && (w0 + cc) < p.W;
-            if (valid) {
-                const int64_t pix = (((int64_t)(n0 + img) * p.H + (h0 + rr)) * p.W + (w0 + cc));
-                const int cbase = nt * BN + half * kCols;
-                const int64_t obase = pix * p.Cout + cbase;
-                const float *bias = p.bias + cbase;
-#pragma unroll
-                for (int j0 = 0; j0 < kCols; j0 += 8) {
-                    float y[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        y[j] = fmaxf(fmaf(acc[j0 + j], p.unscale, __ldg(bias + j0 + j)), 0.0f) * p.out_scale;
-                    if (p.out_f32 != nullptr) {
-                        float4 *dst = reinterpret_cast<float4 *>(p.out_f32 + obase + j0);
-                        dst[0] = make_float4(y[0], y[1], y[2], y[3]);
-                        dst[1] = make_float4(y[4], y[5], y[6], y[7]);
-                    } else {
-                        uint32_t hi[4], lo[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const __half h0v = __float2half_rn(y[2 * j]), h1v = __float2half_rn(y[2 * j + 1]);
-                            const __half l0v = __float2half_rn(y[2 * j] - __half2float(h0v));
-                            const __half l1v = __float2half_rn(y[2 * j + 1] - __half2float(h1v));
-                            hi[j] = (uint32_t)__half_as_ushort(h0v) | ((uint32_t)__half_as_ushort(h1v) << 16);
-                            lo[j] = (uint32_t)__half_as_ushort(l0v) | ((uint32_t)__half_as_ushort(l1v) << 16);
-                        }
-                        *reinterpret_cast<uint4 *>(p.out_hi + obase + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4 *>(p.out_lo + obase + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    }
-                }
-            }
+            store_tile<kCols>(p, acc, tile, tiles_per_group, img, rr, cc, BN, half * kCols, sbias);
         }
     }
     tc_fence_before();
@@ -344,30 +373,178 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
     if (warp == 1) tmem_dealloc(tmem_base, kAccStages * BN);
 }
 
+// ---------------------------------------------------------------- 64 -> 64 channels (block 1, conv2)
+// The generic kernel is bound by the L2 -> SM port on this layer (48 KB of operands per 384 tensor cycles).  Here
+//   * all weights stay resident in shared memory: 9 taps x (B_hi | B_lo) = 144 KB, loaded once per CTA;
+//   * the three taps of one kernel COLUMN kw share one A load: a (BH + 2)-row box at column offset kw - 1 holds
+//     the tiles of kh = 0, 1, 2 at row offsets kh * BW pixels (BW = 16 -> 2 KB steps, swizzle-phase aligned), so
+//     a tile costs 3 x 40 KB of A traffic instead of 9 x 32 KB + 9 x 16 KB;
+//   * per K step two MMAs instead of three:  A_hi x [B_hi ; B_lo] (N = 128: main | correction columns) and
+//     A_lo x B_hi (N = 64, into the correction columns); A_hi is read from shared memory once, not twice.
+// One ring stage = one kw = one accumulation chunk (12 K steps) of the 2-deep TMEM ring.
+constexpr int kC64BoxRows = 10;                                // BH + 2
+constexpr int kC64ABytes = kC64BoxRows * 16 * kSlabK * 2;      // 20 KB per hi / lo box
+constexpr int kC64StageBytes = 2 * kC64ABytes;
+constexpr int kC64BTap = 2 * 64 * kSlabK * 2;                  // B_hi | B_lo of one tap: 16 KB
+constexpr int kC64Stages = 2;
+constexpr int kC64Smem = 9 * kC64BTap + kC64Stages * kC64StageBytes + 1024 + 256 + 64 * 4;
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmAh,
+                                                                      const __grid_constant__ CUtensorMap tmAl,
+                                                                      const __grid_constant__ CUtensorMap tmBh,
+                                                                      const __grid_constant__ CUtensorMap tmBl,
+                                                                      const ConvTcParams p) {
+    constexpr int BN = 64, kCols = BN / 2, kAccCols = 2 * BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *bres = smem;                                   // [9][B_hi 8 KB | B_lo 8 KB]
+    uint8_t *ring = smem + 9 * kC64BTap;                    // [stages][A_hi | A_lo]
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kC64Stages * kC64StageBytes);
+    uint64_t *empty = full + kC64Stages;
+    uint64_t *acc_full = empty + kC64Stages;
+    uint64_t *acc_empty = acc_full + kAccStages;
+    uint64_t *wfull = acc_empty + kAccStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wfull + 1);
+    float *sbias = reinterpret_cast<float *>(ring + kC64Stages * kC64StageBytes + 256);
+    if (threadIdx.x < 64) sbias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_group = p.tilesW * p.tilesH;
+    const int total_tiles = p.mtiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+        for (int i = 0; i < kC64Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
+        mbar_init(wfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kAccStages * kAccCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---------------- TMA producer
+            mbar_expect_tx(wfull, 9 * kC64BTap);
+            for (int t = 0; t < 9; ++t) {
+                tma_load_2d(&tmBh, wfull, bres + t * kC64BTap, t * 64, 0);
+                tma_load_2d(&tmBl, wfull, bres + t * kC64BTap + kC64BTap / 2, t * 64, 0);
+            }
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int grp = tile / tiles_per_group, rem = tile - grp * tiles_per_group;
+                const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+                const int h0 = th * p.BH, w0 = tw * p.BW;
+                for (int kw = 0; kw < 3; ++kw, ++g) {
+                    const uint32_t stage = g % kC64Stages, it = g / kC64Stages;
+                    mbar_wait(&empty[stage], (it & 1) ^ 1);
+                    uint8_t *sb = ring + stage * kC64StageBytes;
+                    mbar_expect_tx(&full[stage], kC64StageBytes);
+                    tma_load_4d(&tmAh, &full[stage], sb, 0, w0 + kw - 1, h0 - 1, grp);
+                    tma_load_4d(&tmAl, &full[stage], sb + kC64ABytes, 0, w0 + kw - 1, h0 - 1, grp);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---------------- MMA issuer
+            constexpr uint32_t idesc_cat = make_idesc(kTileM, 2 * BN), idesc_hi = make_idesc(kTileM, BN);
+            mbar_wait(wfull, 0);
+            tc_fence_after();
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int kw = 0; kw < 3; ++kw, ++g) {
+                    const uint32_t a = g % kAccStages;
+                    mbar_wait(&acc_empty[a], ((g / kAccStages) & 1) ^ 1);
+                    const uint32_t stage = g % kC64Stages, it = g / kC64Stages;
+                    mbar_wait(&full[stage], it & 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + a * kAccCols;
+                    const uint32_t sb = smem_u32(ring + stage * kC64StageBytes);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint64_t a_hi = make_sdesc(sb + kh * (16 * kSlabK * 2));
+                        const uint64_t a_lo = make_sdesc(sb + kC64ABytes + kh * (16 * kSlabK * 2));
+                        const uint64_t b_cat = make_sdesc(smem_u32(bres + (kh * 3 + kw) * kC64BTap));
+#pragma unroll
+                        for (int k = 0; k < kSlabK / 16; ++k) {
+                            umma_f16(d, a_hi + 2 * k, b_cat + 2 * k, idesc_cat, (kh > 0 || k > 0) ? 1u : 0u);
+                            umma_f16(d + BN, a_lo + 2 * k, b_cat + 2 * k, idesc_hi, 1u);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    umma_commit(&acc_full[a]);
+                }
+            }
+        }
+    } else {  // ---------------- epilogue warps 2..9
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int m = q * 32 + lane;
+        const int rr = m / p.BW, cc = m - rr * p.BW;
+        uint32_t c = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            float acc[kCols];
+#pragma unroll
+            for (int j = 0; j < kCols; ++j) acc[j] = 0.0f;
+            for (int ch = 0; ch < 3; ++ch, ++c) {
+                const uint32_t a = c % kAccStages;
+                mbar_wait(&acc_full[a], (c / kAccStages) & 1);
+                tc_fence_after();
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccCols + half * kCols;
+                uint32_t v[32], u[32];
+                tmem_ld32(t0, v);
+                tmem_ld32(t0 + BN, u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < kCols; ++j)
+                    acc[j] = __fadd_rn(acc[j], __fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j])));
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[a]);
+            }
+            store_tile<kCols>(p, acc, tile, tiles_per_group, 0, rr, cc, BN, half * kCols, sbias);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kAccStages * kAccCols);
+}
+
 // ------------------------------------------------------------ SIMT helpers of the fp16x3 path
-// first conv (Cin == 1, K = 9: memory-bound, exact fp32): feat [N][H][W] -> hi/lo NHWC [N][H][W][64]
+// first conv (Cin == 1, K = 9: memory-bound, exact fp32): feat [N][H][W] -> hi/lo NHWC [N][H][W][64].
+// Thread = (pixel, group of 8 output channels); the group is fixed per thread over the grid-stride loop
+// (stride % 8 == 0), so its 72 weights + 8 biases live in registers and the loop is 9 cached loads, 72 FMAs
+// and two 16-byte stores: HBM-write-bound (4 B of hi/lo per output element).
 __global__ void __launch_bounds__(256) tc_conv_first_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                             const float *__restrict__ bias, __half *__restrict__ yh,
                                                             __half *__restrict__ yl, int N, int H, int W) {
-    __shared__ float ws[9][64];
-    __shared__ float bs[64];
-    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) ws[i / 64][i % 64] = w[i];
-    if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
-    __syncthreads();
-    const int64_t total = (int64_t)N * H * W * 8;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int g = (int)(idx & 7);
-        const int64_t pix = idx >> 3;
-        const int wq = (int)(pix % W);
-        const int hq = (int)((pix / W) % H);
-        const int64_t n = pix / ((int64_t)W * H);
+    const int g = threadIdx.x & 7;
+    float wr[9][8], br[8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) wr[t][c] = __ldg(w + t * 64 + g * 8 + c);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) br[c] = __ldg(bias + g * 8 + c);
+    // 32-bit index arithmetic (N*H*W < 2^31 is checked by the launcher): 64-bit div/mod would dominate the loop
+    const uint32_t npix = (uint32_t)N * (uint32_t)H * (uint32_t)W;
+    const uint32_t HW = (uint32_t)H * (uint32_t)W;
+    const uint32_t pstep = (gridDim.x * blockDim.x) >> 3;
+    for (uint32_t pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < npix; pix += pstep) {
+        const uint32_t n = pix / HW;
+        const uint32_t rem = pix - n * HW;
+        const int hq = (int)(rem / (uint32_t)W);
+        const int wq = (int)(rem - (uint32_t)hq * (uint32_t)W);
+        const float *xn = x + (size_t)n * HW;
         float v[9];
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
                 const int hh = hq + kh - 1, ww = wq + kw - 1;
-                v[kh * 3 + kw] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + (n * H + hh) * W + ww) : 0.0f;
+                v[kh * 3 + kw] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xn + hh * W + ww) : 0.0f;
             }
         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -375,48 +552,18 @@ __global__ void __launch_bounds__(256) tc_conv_first_kernel(const float *__restr
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-                a0 = fmaf(v[t], ws[t][g * 8 + 2 * c2], a0);
-                a1 = fmaf(v[t], ws[t][g * 8 + 2 * c2 + 1], a1);
+                a0 = fmaf(v[t], wr[t][2 * c2], a0);
+                a1 = fmaf(v[t], wr[t][2 * c2 + 1], a1);
             }
-            a0 = fmaxf(a0 + bs[g * 8 + 2 * c2], 0.f) * kActScale;
-            a1 = fmaxf(a1 + bs[g * 8 + 2 * c2 + 1], 0.f) * kActScale;
+            a0 = fmaxf(a0 + br[2 * c2], 0.f) * kActScale;
+            a1 = fmaxf(a1 + br[2 * c2 + 1], 0.f) * kActScale;
             const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
             const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
             hi[c2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
             lo[c2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
         }
-        *reinterpret_cast<uint4 *>(yh + pix * 64 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4 *>(yl + pix * 64 + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-}
-
-// 2x2 average pool of the fp32 conv2 output -> fp16 hi/lo input of the next block
-__global__ void __launch_bounds__(256) tc_pool_split_kernel(const float *__restrict__ x, __half *__restrict__ yh,
-                                                            __half *__restrict__ yl, int N, int H, int W, int C) {
-    const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
-    const int64_t total = (int64_t)N * Ho * Wo * C4;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(idx % C4);
-        const int64_t pix = idx / C4;
-        const int wo = (int)(pix % Wo);
-        const int ho = (int)((pix / Wo) % Ho);
-        const int64_t n = pix / ((int64_t)Wo * Ho);
-        const float4 *src = reinterpret_cast<const float4 *>(x + ((n * H + 2 * ho) * W + 2 * wo) * C) + c4;
-        const float4 a = __ldg(src), b = __ldg(src + C4);
-        const float4 c = __ldg(src + (int64_t)W * C4), d = __ldg(src + (int64_t)W * C4 + C4);
-        constexpr float k = 0.25f * kActScale;  // exact powers of two
-        const float o[4] = {((a.x + b.x) + (c.x + d.x)) * k, ((a.y + b.y) + (c.y + d.y)) * k,
-                            ((a.z + b.z) + (c.z + d.z)) * k, ((a.w + b.w) + (c.w + d.w)) * k};
-        uint32_t hi[2], lo[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const __half h0 = __float2half_rn(o[2 * j]), h1 = __float2half_rn(o[2 * j + 1]);
-            const __half l0 = __float2half_rn(o[2 * j] - __half2float(h0)), l1 = __float2half_rn(o[2 * j + 1] - __half2float(h1));
-            hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-        }
-        *reinterpret_cast<uint2 *>(yh + idx * 4) = make_uint2(hi[0], hi[1]);
-        *reinterpret_cast<uint2 *>(yl + idx * 4) = make_uint2(lo[0], lo[1]);
+        *reinterpret_cast<uint4 *>(yh + (size_t)pix * 64 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(yl + (size_t)pix * 64 + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -493,7 +640,7 @@ int num_sms() {
 template <int BN, int STAGES>
 int launch_conv_tc_t(cudaStream_t st, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh,
                      const CUtensorMap &bl, const ConvTcParams &p) {
-    constexpr int smem = STAGES * (2 * kABytes + 2 * BN * kSlabK * 2) + 1024 + 256;
+    constexpr int smem = STAGES * (2 * kABytes + 2 * BN * kSlabK * 2) + 1024 + 256 + 2048 * 4;  // ring, align, barriers, bias
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -527,6 +674,12 @@ int chunk_slabs() {
         if (const char *e = getenv("STITO_TC_CHUNK")) { const int t = atoi(e); if (t > 0) v = t; }
     }
     return v;
+}
+
+bool use_c64() {  // STITO_TC_C64=0 falls back to the generic kernel for block 1 (developer knob)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("STITO_TC_C64"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v != 0;
 }
 
 inline int blocks_for(int64_t total, int threads) {
@@ -587,13 +740,16 @@ void tc_workspace_release(TcWorkspace *ws) {
 
 // One conv layer on tensor cores: in (hi, lo) NHWC [N][H][W][Cin] -> out fp16 pair or fp32.
 static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, const __half *in_lo, __half *out_hi,
-                   __half *out_lo, float *out_f32, int N, int H, int W, int *launches) {
+                   __half *out_lo, float *out_f32, int N, int H, int W, bool pool, int *launches) {
     ConvTcParams p{};
     p.bias = l.bias; p.unscale = l.w_unscale / kActScale;
-    p.out_scale = out_f32 ? 1.0f : kActScale;
+    p.out_scale = out_f32 ? 1.0f : (pool ? 0.25f * kActScale : kActScale);  // exact powers of two
+    p.pool = pool ? 1 : 0;
     p.out_hi = out_hi; p.out_lo = out_lo; p.out_f32 = out_f32;
     p.N = N; p.H = H; p.W = W; p.Cin = l.cin; p.Cout = l.cout;
     p.BW = W < 64 ? W : 64;
+    if (pool && p.BW > 16) p.BW = 16;  // keeps every 2x2 window inside one warp of the epilogue
+    if (pool && (p.BW & (p.BW - 1)) != 0) return tc_fail("conv_tc", "pooled layers need a power-of-two tile width");
     int bh = kTileM / p.BW;
     if (bh > H) bh = H;
     p.BH = bh;
@@ -608,9 +764,28 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, con
     p.mtiles = groups * p.tilesW * p.tilesH;
     p.ntiles = l.cout / BN;
     p.chunk_slabs = chunk_slabs();
-    if (l.cin % kSlabK != 0 || l.cout % BN != 0 || (BN != 64 && BN != 128 && BN != 256))
+    if (l.cin % kSlabK != 0 || l.cout % BN != 0 || l.cout > 2048 || (BN != 64 && BN != 128 && BN != 256))
         return tc_fail("conv_tc", "unsupported channel counts");
     CUtensorMap ah, al, bh_, bl;
+    if (l.cin == 64 && l.cout == 64 && p.BW == 16 && p.BH == 8 && p.IPT == 1 && use_c64()) {
+        // resident weights + kh-shared A boxes (conv3x3_c64_kernel)
+        if (make_act_map(&ah, in_hi, N, H, W, 64, 16, kC64BoxRows, 1)) return -1;
+        if (make_act_map(&al, in_lo, N, H, W, 64, 16, kC64BoxRows, 1)) return -1;
+        if (make_w_map(&bh_, l.w_hi, 64, 9 * 64, 64)) return -1;
+        if (make_w_map(&bl, l.w_lo, 64, 9 * 64, 64)) return -1;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(conv3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC64Smem);
+            if (e != cudaSuccess) return tc_fail("cudaFuncSetAttribute", cudaGetErrorString(e));
+            configured = true;
+        }
+        const int grid = p.mtiles < num_sms() ? p.mtiles : num_sms();
+        conv3x3_c64_kernel<<<grid, kConvThreads, kC64Smem, st>>>(ah, al, bh_, bl, p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return tc_fail("conv3x3_c64_kernel launch", cudaGetErrorString(e));
+        *launches += 1;
+        return 0;
+    }
     if (make_act_map(&ah, in_hi, N, H, W, l.cin, p.BW, p.BH, p.IPT)) return -1;
     if (make_act_map(&al, in_lo, N, H, W, l.cin, p.BW, p.BH, p.IPT)) return -1;
     if (make_w_map(&bh_, l.w_hi, l.cout, 9 * l.cin, BN)) return -1;
@@ -625,12 +800,12 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, con
 
 int tc_encoder_forward(cudaStream_t st, const EncoderDev &enc, TcWorkspace &ws, const float *feat, int N, int T,
                        int mel, float *pooled, int *launches, cudaEvent_t *ev) {
-    // workspace: [0],[1] = hi/lo activations A, [2] = hi+lo activations B (conv1 outputs), [3] = fp32 conv2 output
+    // workspace: [0],[1] = hi/lo block inputs (pooled), [2] = hi+lo conv1 outputs, [3] = fp32 output of block 6
     const size_t px0 = (size_t)N * T * mel;
     if (ws_ensure(ws, 0, px0 * 16 * sizeof(__half))) return -1;  // block input (pooled) hi: largest is block 2, px0/4 x 64
     if (ws_ensure(ws, 1, px0 * 16 * sizeof(__half))) return -1;  // lo
     if (ws_ensure(ws, 2, 2 * px0 * 64 * sizeof(__half))) return -1;  // conv1 output hi | lo
-    if (ws_ensure(ws, 3, px0 * 64 * sizeof(float))) return -1;   // conv2 output fp32
+    if (ws_ensure(ws, 3, (size_t)N * (T >> 5) * (mel >> 5) * 2048 * sizeof(float))) return -1;  // block-6 output fp32
     __half *in_hi = (__half *)ws.buf[0], *in_lo = (__half *)ws.buf[1];
     float *c2 = (float *)ws.buf[3];
     int H = T, W = mel;
@@ -640,19 +815,19 @@ int tc_encoder_forward(cudaStream_t st, const EncoderDev &enc, TcWorkspace &ws, 
         __half *m_hi = (__half *)ws.buf[2], *m_lo = m_hi + px * l1.cout;
         if (ev) cudaEventRecord(ev[2 * b], st);
         if (b == 0) {
+            if ((uint64_t)px >= (1ull << 31)) return tc_fail("tc_encoder_forward", "micro-batch too large for 32-bit pixel indices");
             tc_conv_first_kernel<<<blocks_for((int64_t)px * 8, 256), 256, 0, st>>>(feat, l1.w, l1.bias, m_hi, m_lo, N, H, W);
             *launches += 1;
         } else {
-            if (conv_tc(st, l1, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, launches)) return -1;
+            if (conv_tc(st, l1, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
         }
         if (ev) cudaEventRecord(ev[2 * b + 1], st);
-        if (conv_tc(st, l2, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, launches)) return -1;
-        if (b < 5) {
-            const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (l2.cout / 4);
-            tc_pool_split_kernel<<<blocks_for(total, 256), 256, 0, st>>>(c2, in_hi, in_lo, N, H, W, l2.cout);
-            *launches += 1;
+        if (b < 5) {  // conv2 + ReLU + 2x2 average pool + hi/lo split in one kernel -> next block's input
+            if (conv_tc(st, l2, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
             H /= 2;
             W /= 2;
+        } else {
+            if (conv_tc(st, l2, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, false, launches)) return -1;
         }
     }
     if (ev) cudaEventRecord(ev[12], st);
