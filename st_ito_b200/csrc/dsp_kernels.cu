@@ -130,48 +130,88 @@ __global__ void __launch_bounds__(128) eq_chunk_kernel(SigView in, const float *
     }
 }
 
-// One warp per stream: S[k+1] = M * S[k] + F[k], S[0] = 0, where M is the zero-input transition of
-// the 12-state cascade over one full chunk.  Lane i < 12 owns row i of M and component i of S.
-__global__ void __launch_bounds__(32) eq_stitch_kernel(int chs, int K, const double *coefs,
-                                                       const double *zs_final, double *init) {
+// Stitch: S[k+1] = M * S[k] + F[k], S[0] = 0, where M (12 x 12) is the zero-input transition of the 12-state
+// cascade over one full chunk and F[k] the zero-state final state of chunk k.  The scan itself is sequential
+// (lane i < 12 of warp 0 owns row i of M and component i of S; ~100 cycles per chunk): the cascade's transition
+// matrix is far from normal (states of a 20 Hz biquad are huge and cancel), and re-associating the scan through
+// powers of M costs ~2 decimal digits, enough to flip the float32 rounding of a third of the output samples.
+// What made the old one-warp kernel slow (0.35 ms) was not arithmetic but one dependent global load of F per
+// step; here the CTA stages F in shared memory in tiles of 1024 chunks (coalesced), overlapped with the
+// construction of M, and S overwrites F in place and is written back coalesced.
+constexpr int kStitchThreads = 512;
+constexpr int kStitchTile = 1024;  // chunks per shared-memory tile: 12 x 1024 x 8 B = 96 KB
+
+__device__ __forceinline__ double stitch_matvec(const double (&row)[kEqStates], double s, double f) {
+    double a0 = f, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < kEqStates; j += 3) {
+        a0 = fma(row[j], __shfl_sync(0xffffffffu, s, j), a0);
+        a1 = fma(row[j + 1], __shfl_sync(0xffffffffu, s, j + 1), a1);
+        a2 = fma(row[j + 2], __shfl_sync(0xffffffffu, s, j + 2), a2);
+    }
+    return a0 + (a1 + a2);
+}
+
+__global__ void __launch_bounds__(kStitchThreads) eq_stitch_kernel(int chs, int K, const double *coefs,
+                                                                    const double *zs_final, double *init) {
+    extern __shared__ double fs[];                      // [kEqStates][kStitchTile]
     __shared__ double Msm[kEqStates][kEqStates + 1];
     const int stream = blockIdx.x;
     const int p = stream / chs;
-    const int lane = threadIdx.x;
-    double cf[6][5];
-    eq_load_coefs(coefs, p, cf);
-    if (lane < kEqStates) {  // column `lane` of M: propagate the basis state e_lane for one chunk
-        double z0[6], z1[6];
-#pragma unroll
-        for (int s = 0; s < 6; ++s) {
-            z0[s] = (lane == 2 * s) ? 1.0 : 0.0;
-            z1[s] = (lane == 2 * s + 1) ? 1.0 : 0.0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *F = zs_final + (int64_t)stream * kEqStates * K;
+    double *S = init + (int64_t)stream * kEqStates * K;
+    auto load_tile = [&](int t0, int nt, int first, int nthreads) {
+        for (int idx = first; idx < kEqStates * nt; idx += nthreads) {
+            const int r = idx / nt, k = idx - r * nt;
+            fs[r * kStitchTile + k] = F[(int64_t)r * K + t0 + k];
         }
-        for (int i = 0; i < kEqChunk; ++i) (void)eq_step(0.0, cf, z0, z1);
+    };
+    if (warp == 0) {
+        if (lane < kEqStates) {  // column `lane` of M: propagate the basis state e_lane for one chunk
+            double cf[6][5];
+            eq_load_coefs(coefs, p, cf);
+            double z0[6], z1[6];
 #pragma unroll
-        for (int s = 0; s < 6; ++s) { Msm[2 * s][lane] = z0[s]; Msm[2 * s + 1][lane] = z1[s]; }
+            for (int s = 0; s < 6; ++s) {
+                z0[s] = (lane == 2 * s) ? 1.0 : 0.0;
+                z1[s] = (lane == 2 * s + 1) ? 1.0 : 0.0;
+            }
+            for (int i = 0; i < kEqChunk; ++i) (void)eq_step(0.0, cf, z0, z1);
+#pragma unroll
+            for (int s = 0; s < 6; ++s) { Msm[2 * s][lane] = z0[s]; Msm[2 * s + 1][lane] = z1[s]; }
+        }
+    } else {
+        load_tile(0, min(kStitchTile, K), tid - 32, kStitchThreads - 32);  // meanwhile, warps 1.. stage the first tile
     }
-    __syncwarp();
-    double row[kEqStates];
+    __syncthreads();
     const int r = lane < kEqStates ? lane : 0;
+    double row[kEqStates];
 #pragma unroll
     for (int j = 0; j < kEqStates; ++j) row[j] = Msm[r][j];
-    const double *F = zs_final + ((int64_t)stream * kEqStates + r) * K;
-    double *S = init + ((int64_t)stream * kEqStates + r) * K;
     double s = 0.0;
-    double fnext = K > 0 ? F[0] : 0.0;
-    for (int k = 0; k < K; ++k) {
-        if (lane < kEqStates) S[k] = s;
-        const double f = fnext;
-        if (k + 1 < K) fnext = F[k + 1];
-        double a0 = f, a1 = 0.0, a2 = 0.0;
-#pragma unroll
-        for (int j = 0; j < kEqStates; j += 3) {
-            a0 = fma(row[j], __shfl_sync(0xffffffffu, s, j), a0);
-            a1 = fma(row[j + 1], __shfl_sync(0xffffffffu, s, j + 1), a1);
-            a2 = fma(row[j + 2], __shfl_sync(0xffffffffu, s, j + 2), a2);
+    for (int t0 = 0; t0 < K; t0 += kStitchTile) {
+        const int nt = min(kStitchTile, K - t0);
+        if (t0 > 0) {
+            load_tile(t0, nt, tid, kStitchThreads);
+            __syncthreads();
         }
-        s = a0 + (a1 + a2);
+        if (warp == 0) {
+            double *fr = fs + r * kStitchTile;
+            double fnext = fr[0];
+            for (int k = 0; k < nt; ++k) {
+                const double f = fnext;
+                if (k + 1 < nt) fnext = fr[k + 1];
+                if (lane < kEqStates) fr[k] = s;  // S[k] replaces F[k]
+                s = stitch_matvec(row, s, f);
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < kEqStates * nt; idx += kStitchThreads) {
+            const int rr = idx / nt, k = idx - rr * nt;
+            S[(int64_t)rr * K + t0 + k] = fs[rr * kStitchTile + k];
+        }
+        __syncthreads();
     }
 }
 
@@ -781,7 +821,16 @@ cudaError_t launch_eq(cudaStream_t st, SigView in, const float *in_peak, float *
     const int streams = P * chs;
     dim3 grid((K + 127) / 128, streams);
     eq_chunk_kernel<false><<<grid, 128, 0, st>>>(in, in_peak, nullptr, chs, L, K, coefs, scratch_f, nullptr);
-    eq_stitch_kernel<<<streams, 32, 0, st>>>(chs, K, coefs, scratch_f, scratch_s);
+    {
+        constexpr int smem = kEqStates * kStitchTile * (int)sizeof(double);
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(eq_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        eq_stitch_kernel<<<streams, kStitchThreads, smem, st>>>(chs, K, coefs, scratch_f, scratch_s);
+    }
     eq_chunk_kernel<true><<<grid, 128, 0, st>>>(in, in_peak, out, chs, L, K, coefs, scratch_s, out_peak);
     *launches += 3;
     return cudaGetLastError();

@@ -514,9 +514,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_c64_kernel(const __gr
 
 // ------------------------------------------------------------ SIMT helpers of the fp16x3 path
 // first conv (Cin == 1, K = 9: memory-bound, exact fp32): feat [N][H][W] -> hi/lo NHWC [N][H][W][64].
-// Thread = (pixel, group of 8 output channels); the group is fixed per thread over the grid-stride loop
-// (stride % 8 == 0), so its 72 weights + 8 biases live in registers and the loop is 9 cached loads, 72 FMAs
-// and two 16-byte stores: HBM-write-bound (4 B of hi/lo per output element).
+// Thread = (4 horizontally adjacent pixels, group of 8 output channels).  The channel group is fixed per thread
+// over the grid-stride loop (stride % 8 == 0), so its 72 weights + 8 biases live in registers; per iteration a
+// thread reads a 3 x 6 input patch (cached loads, shared by its 4 pixels), does 288 FMAs and writes 4 x 2 x 16 B.
+constexpr int kC1Px = 4;
 __global__ void __launch_bounds__(256) tc_conv_first_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                             const float *__restrict__ bias, __half *__restrict__ yh,
                                                             __half *__restrict__ yl, int N, int H, int W) {
@@ -529,41 +530,51 @@ __global__ void __launch_bounds__(256) tc_conv_first_kernel(const float *__restr
 #pragma unroll
     for (int c = 0; c < 8; ++c) br[c] = __ldg(bias + g * 8 + c);
     // 32-bit index arithmetic (N*H*W < 2^31 is checked by the launcher): 64-bit div/mod would dominate the loop
-    const uint32_t npix = (uint32_t)N * (uint32_t)H * (uint32_t)W;
-    const uint32_t HW = (uint32_t)H * (uint32_t)W;
-    const uint32_t pstep = (gridDim.x * blockDim.x) >> 3;
-    for (uint32_t pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < npix; pix += pstep) {
-        const uint32_t n = pix / HW;
-        const uint32_t rem = pix - n * HW;
-        const int hq = (int)(rem / (uint32_t)W);
-        const int wq = (int)(rem - (uint32_t)hq * (uint32_t)W);
-        const float *xn = x + (size_t)n * HW;
-        float v[9];
+    const uint32_t Wq = (uint32_t)(W + kC1Px - 1) / kC1Px;          // pixel quads per row
+    const uint32_t nquads = (uint32_t)N * (uint32_t)H * Wq;
+    const uint32_t qstep = (gridDim.x * blockDim.x) >> 3;
+    for (uint32_t quad = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; quad < nquads; quad += qstep) {
+        const uint32_t row = quad / Wq;                               // n * H + h
+        const int w0 = (int)(quad - row * Wq) * kC1Px;
+        const uint32_t n = row / (uint32_t)H;
+        const int hq = (int)(row - n * (uint32_t)H);
+        const float *xn = x + (size_t)n * H * W;
+        float v[3][kC1Px + 2];
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hh = hq + kh - 1;
+            const bool hok = hh >= 0 && hh < H;
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int hh = hq + kh - 1, ww = wq + kw - 1;
-                v[kh * 3 + kw] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xn + hh * W + ww) : 0.0f;
+            for (int i = 0; i < kC1Px + 2; ++i) {
+                const int ww = w0 + i - 1;
+                v[kh][i] = (hok && ww >= 0 && ww < W) ? __ldg(xn + hh * W + ww) : 0.0f;
             }
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int c2 = 0; c2 < 4; ++c2) {
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                a0 = fmaf(v[t], wr[t][2 * c2], a0);
-                a1 = fmaf(v[t], wr[t][2 * c2 + 1], a1);
-            }
-            a0 = fmaxf(a0 + br[2 * c2], 0.f) * kActScale;
-            a1 = fmaxf(a1 + br[2 * c2 + 1], 0.f) * kActScale;
-            const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
-            const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
-            hi[c2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            lo[c2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
         }
-        *reinterpret_cast<uint4 *>(yh + (size_t)pix * 64 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4 *>(yl + (size_t)pix * 64 + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+        for (int px = 0; px < kC1Px; ++px) {
+            if (w0 + px >= W) break;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int c2 = 0; c2 < 4; ++c2) {
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {  // same accumulation order as the single-pixel form (t = 0..8)
+                        a0 = fmaf(v[kh][px + kw], wr[kh * 3 + kw][2 * c2], a0);
+                        a1 = fmaf(v[kh][px + kw], wr[kh * 3 + kw][2 * c2 + 1], a1);
+                    }
+                a0 = fmaxf(a0 + br[2 * c2], 0.f) * kActScale;
+                a1 = fmaxf(a1 + br[2 * c2 + 1], 0.f) * kActScale;
+                const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+                const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+                hi[c2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                lo[c2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            const size_t o = ((size_t)row * W + w0 + px) * 64 + g * 8;
+            *reinterpret_cast<uint4 *>(yh + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(yl + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
     }
 }
 
@@ -816,7 +827,7 @@ int tc_encoder_forward(cudaStream_t st, const EncoderDev &enc, TcWorkspace &ws, 
         if (ev) cudaEventRecord(ev[2 * b], st);
         if (b == 0) {
             if ((uint64_t)px >= (1ull << 31)) return tc_fail("tc_encoder_forward", "micro-batch too large for 32-bit pixel indices");
-            tc_conv_first_kernel<<<blocks_for((int64_t)px * 8, 256), 256, 0, st>>>(feat, l1.w, l1.bias, m_hi, m_lo, N, H, W);
+            tc_conv_first_kernel<<<blocks_for((int64_t)px * 8 / kC1Px, 256), 256, 0, st>>>(feat, l1.w, l1.bias, m_hi, m_lo, N, H, W);
             *launches += 1;
         } else {
             if (conv_tc(st, l1, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
