@@ -273,19 +273,38 @@ def run_ours(args, rank, world, local_rank):
     K = args.steps
     value = world * P * K / (ms / 1e3)
     e2e_value = world * P * K / (ms_e2e / 1e3)
-    enc_ms = stage["ms_encoder"] / K
-    flop = last["encoder_flop"]
     tc = last["precision"] == 1
-    achieved = flop / (enc_ms / 1e3) / 1e12 if enc_ms > 0 else 0.0
+    # dominant kernel: the tcgen05 implicit-GEMM convolution (11 launches per generation: conv layers 2..12; layer 1,
+    # Cin = 1 / K = 9, is a separate memory-bound CUDA-core kernel).  Algorithmic FLOPs of those launches / their
+    # CUDA-event time on the launch stream (per-layer events recorded inside libstito).
+    T = L // 1024 + 1
+    ch = [1, 64, 128, 256, 512, 1024, 2048]
+    layer_flop, hh, ww = [], T, 128
+    for b in range(6):
+        layer_flop += [2.0 * hh * ww * ch[b + 1] * 9 * ch[b], 2.0 * hh * ww * ch[b + 1] * 9 * ch[b + 1]]
+        hh, ww = hh // 2, ww // 2
+    layer_flop = [f * 2 * P for f in layer_flop]  # 2 signals (mid, side) per stereo candidate
+    ms_layers = [float(v) / K for v in conv_ms]
+    tc_flop, tc_ms = sum(layer_flop[1:]), sum(ms_layers[1:])
+    achieved = tc_flop / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     peak = peaks["tflops_sustained"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01b_conv_traffic.json")
+    if tc and P == 64 and abs(args.seconds - 10.0) < 1e-9 and os.path.isfile(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)["dram_bytes_per_generation"] / 11.0  # per launch, like `achieved`
     roofline = {
-        "kernel": "AFx-Rep conv stack (12 x conv3x3 implicit GEMM, " + ("fp16x3 tcgen05" if tc else "fp32 CUDA cores") + ")",
+        "kernel": ("conv3x3_tc_kernel / conv3x3_c64_kernel (tcgen05 implicit-GEMM 3x3 conv, fp16x3 split precision), "
+                   "11 launches per generation") if tc else "conv3x3 fp32 CUDA-core kernel (precision 0)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": f"{peaks['source']} bf16 sustained",
-        "note": "achieved = algorithmic 2*MAC of the 12 convolutions (74.45 GFLOP per stereo 10 s candidate) / "
-                "CUDA-event time of the conv stack on the launch stream; fp16x3 issues 3 tensor-core MACs per "
-                "algorithmic MAC" if tc else "fp32 CUDA-core mode (exact-arithmetic reference mode of the library)",
-        "ms_per_layer": [float(v) / K for v in conv_ms],
+        "traffic": traffic, "traffic_unit": "bytes per launch (mean of the 11 launches; ncu dram read+write, "
+                                            "profiles/r01b_conv_traffic.json)",
+        "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)",
+        "note": "achieved = algorithmic 2*MAC of conv layers 2..12 (%.2f GFLOP per stereo candidate) / CUDA-event time "
+                "of those launches; the fp16x3 scheme executes 3 tensor-core MACs per algorithmic MAC, i.e. the tensor "
+                "pipes run at 3x `achieved`" % (tc_flop / P / 1e9),
+        "tensor_pipe_executed_tflops": 3.0 * achieved if tc else None,
+        "ms_per_layer": ms_layers,
         "stages_ms": {k: v / K for k, v in stage.items()},
         "hbm": {"dsp_GBps": last["dsp_bytes"] / max(stage["ms_dsp"] / K, 1e-9) / 1e6,
                 "frontend_GBps": last["frontend_bytes"] / max(stage["ms_frontend"] / K, 1e-9) / 1e6,
