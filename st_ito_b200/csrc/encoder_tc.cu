@@ -126,6 +126,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // UMMA shared-memory descriptor: K-major, 128-byte swizzle, 128-byte rows, 8-row groups 1024 B apart
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30) = 0, SBO>>4 [32,46) = 64, version [46,48) = 1,
 //  layout_type [61,64) = 2 (SWIZZLE_128B)).
+// SLABK = 32 uses the 64-byte swizzle instead (64-byte rows, 8-row groups 512 B apart, layout_type = 4).
+template <int SLABK>
+__device__ __forceinline__ uint64_t make_sdesc_k(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((8 * SLABK * 2) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(SLABK == 64 ? 2 : 4) << 61;
+    return d;
+}
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
     uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)(1024 >> 4) << 32;
@@ -157,7 +166,6 @@ struct ConvTcParams {
 
 constexpr int kTileM = 128;
 constexpr int kSlabK = 64;                       // fp16 elements = one 128-byte swizzle row
-constexpr int kABytes = kTileM * kSlabK * 2;     // 16 KB
 constexpr int kEpiWarps = 8;                     // 4 TMEM lane quarters x 2 column halves
 constexpr int kConvThreads = 32 * (2 + kEpiWarps);
 constexpr int kAccStages = 2;                    // TMEM accumulator ring
@@ -241,13 +249,14 @@ __device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&
 //               fp32 register accumulators with round-to-nearest on the CUDA cores while the next chunk is
 //               being multiplied.  After the last chunk: * unscale + bias, ReLU, fp16 hi/lo split (or fp32)
 //               and the NHWC store.  The drain of tile i's last chunk overlaps the MMAs of tile i+1.
-template <int BN, int STAGES>
+template <int BN, int STAGES, int SLABK>
 __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmAh,
                                                                      const __grid_constant__ CUtensorMap tmAl,
                                                                      const __grid_constant__ CUtensorMap tmBh,
                                                                      const __grid_constant__ CUtensorMap tmBl,
                                                                      const ConvTcParams p) {
-    constexpr int kBBytes = BN * kSlabK * 2;
+    constexpr int kABytes = kTileM * SLABK * 2;
+    constexpr int kBBytes = BN * SLABK * 2;
     constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
     constexpr int kCols = BN / 2;  // accumulator columns owned by one epilogue thread
     extern __shared__ uint8_t smem_raw[];
@@ -263,7 +272,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_group = p.tilesW * p.tilesH;
     const int total_tiles = p.mtiles * p.ntiles;
-    const int cpt = p.Cin / kSlabK;  // channel slabs per tap
+    const int cpt = p.Cin / SLABK;  // channel slabs per tap
     const int nslabs = 9 * cpt;
     const int nchunks = (nslabs + p.chunk_slabs - 1) / p.chunk_slabs;
 
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
 
     if (warp == 0) {
         if (lane == 0) {  // ---------------- TMA producer
-            const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.IPT) * kSlabK * 2;
+            const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.IPT) * SLABK * 2;
             const uint32_t tx_bytes = 2 * a_box_bytes + 2 * kBBytes;
             uint32_t g = 0;  // slabs issued so far (ring position), continues across tiles
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -294,7 +303,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                     mbar_wait(&empty[stage], (it & 1) ^ 1);  // passes at once on the first lap
                     uint8_t *sb = smem + stage * kStageBytes;
                     mbar_expect_tx(&full[stage], tx_bytes);
-                    const int tap = s / cpt, c0 = (s - tap * cpt) * kSlabK;
+                    const int tap = s / cpt, c0 = (s - tap * cpt) * SLABK;
                     const int kh = tap / 3, kw = tap - kh * 3;
                     tma_load_4d(&tmAh, &full[stage], sb, c0, w0 + kw - 1, h0 + kh - 1, n0);
                     tma_load_4d(&tmAl, &full[stage], sb + kABytes, c0, w0 + kw - 1, h0 + kh - 1, n0);
@@ -319,16 +328,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                         mbar_wait(&full[stage], it & 1);
                         tc_fence_after();
                         const uint32_t sb = smem_u32(smem + stage * kStageBytes);
-                        const uint64_t a_hi = make_sdesc(sb), a_lo = make_sdesc(sb + kABytes);
-                        const uint64_t b_hi = make_sdesc(sb + 2 * kABytes), b_lo = make_sdesc(sb + 2 * kABytes + kBBytes);
+                        const uint64_t a_hi = make_sdesc_k<SLABK>(sb), a_lo = make_sdesc_k<SLABK>(sb + kABytes);
+                        const uint64_t b_hi = make_sdesc_k<SLABK>(sb + 2 * kABytes), b_lo = make_sdesc_k<SLABK>(sb + 2 * kABytes + kBBytes);
                         // small terms first: they meet the accumulator while it is small
 #pragma unroll
-                        for (int k = 0; k < kSlabK / 16; ++k)  // +32 B per K step of 16 inside the swizzle atom
+                        for (int k = 0; k < SLABK / 16; ++k)  // +32 B per K step of 16 inside the swizzle atom
                             umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, idesc, (s > s0 || k > 0) ? 1u : 0u);
 #pragma unroll
-                        for (int k = 0; k < kSlabK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                        for (int k = 0; k < SLABK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
-                        for (int k = 0; k < kSlabK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                        for (int k = 0; k < SLABK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
                         umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
                     }
                     umma_commit(&acc_full[a]);  // chunk complete -> epilogue may drain it
@@ -601,15 +610,17 @@ int tc_fail(const char *what, const char *detail) {
 }
 
 // activations: fp16 NHWC viewed as 4-D (C, W, H, N), box (64, BW, BH, IPT), 128B swizzle, zero OOB fill
-int make_act_map(CUtensorMap *m, const void *base, int N, int H, int W, int C, int BW, int BH, int IPT) {
+int make_act_map(CUtensorMap *m, const void *base, int N, int H, int W, int C, int BW, int BH, int IPT,
+                 int slabk = kSlabK) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return tc_fail("cuTensorMapEncodeTiled", "driver entry point not found");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kSlabK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)IPT};
+    cuuint32_t box[4] = {(cuuint32_t)slabk, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)IPT};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, slabk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[160];
@@ -620,15 +631,16 @@ int make_act_map(CUtensorMap *m, const void *base, int N, int H, int W, int C, i
 }
 
 // weights: fp16 [Cout][K] K-major, box (64, BN)
-int make_w_map(CUtensorMap *m, const void *base, int Cout, int K, int BN) {
+int make_w_map(CUtensorMap *m, const void *base, int Cout, int K, int BN, int slabk = kSlabK) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return tc_fail("cuTensorMapEncodeTiled", "driver entry point not found");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kSlabK, (cuuint32_t)BN};
+    cuuint32_t box[2] = {(cuuint32_t)slabk, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, slabk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[128];
@@ -648,19 +660,19 @@ int num_sms() {
     return n;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int SLABK>
 int launch_conv_tc_t(cudaStream_t st, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh,
                      const CUtensorMap &bl, const ConvTcParams &p) {
-    constexpr int smem = STAGES * (2 * kABytes + 2 * BN * kSlabK * 2) + 1024 + 256 + 2048 * 4;  // ring, align, barriers, bias
+    constexpr int smem = STAGES * (2 * kTileM * SLABK * 2 + 2 * BN * SLABK * 2) + 1024 + 256 + 2048 * 4;  // ring, align, barriers, bias
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES, SLABK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return tc_fail("cudaFuncSetAttribute", cudaGetErrorString(e));
         configured = true;
     }
     const int total = p.mtiles * p.ntiles;
     const int grid = total < num_sms() ? total : num_sms();  // persistent: one CTA per SM
-    conv3x3_tc_kernel<BN, STAGES><<<grid, kConvThreads, smem, st>>>(ah, al, bh, bl, p);
+    conv3x3_tc_kernel<BN, STAGES, SLABK><<<grid, kConvThreads, smem, st>>>(ah, al, bh, bl, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tc_fail("conv3x3_tc_kernel launch", cudaGetErrorString(e));
     return 0;
@@ -685,6 +697,18 @@ int chunk_slabs() {
         if (const char *e = getenv("STITO_TC_CHUNK")) { const int t = atoi(e); if (t > 0) v = t; }
     }
     return v;
+}
+
+int slab_k(int cin) {
+    // measured on B200 (P = 64, 10 s): K = 32 wins on the deep layers (Cin >= 1024: -9 % b5c2, -8 % b6c1, -10 % b6c2),
+    // K = 64 on the wide, shallow ones (fewer TMA / barrier round trips per byte)
+    static int forced = -1;
+    if (forced < 0) {
+        forced = 0;
+        if (const char *e = getenv("STITO_TC_SLABK")) { const int t = atoi(e); if (t == 32 || t == 64) forced = t; }
+    }
+    if (forced) return forced;
+    return cin >= 1024 ? 32 : 64;
 }
 
 bool use_c64() {  // STITO_TC_C64=0 falls back to the generic kernel for block 1 (developer knob)
@@ -797,14 +821,24 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, con
         *launches += 1;
         return 0;
     }
-    if (make_act_map(&ah, in_hi, N, H, W, l.cin, p.BW, p.BH, p.IPT)) return -1;
-    if (make_act_map(&al, in_lo, N, H, W, l.cin, p.BW, p.BH, p.IPT)) return -1;
-    if (make_w_map(&bh_, l.w_hi, l.cout, 9 * l.cin, BN)) return -1;
-    if (make_w_map(&bl, l.w_lo, l.cout, 9 * l.cin, BN)) return -1;
+    // K-slab per ring stage: 32 (64-byte swizzle, twice as many stages in the same shared memory: the producer runs
+    // further ahead of the MMA issuer) or 64 (128-byte swizzle), chosen per layer; STITO_TC_SLABK overrides
+    const int slabk = slab_k(l.cin);
+    p.chunk_slabs = chunk_slabs() * (64 / slabk);
+    if (make_act_map(&ah, in_hi, N, H, W, l.cin, p.BW, p.BH, p.IPT, slabk)) return -1;
+    if (make_act_map(&al, in_lo, N, H, W, l.cin, p.BW, p.BH, p.IPT, slabk)) return -1;
+    if (make_w_map(&bh_, l.w_hi, l.cout, 9 * l.cin, BN, slabk)) return -1;
+    if (make_w_map(&bl, l.w_lo, l.cout, 9 * l.cin, BN, slabk)) return -1;
     int rc;
-    if (BN == 64) rc = launch_conv_tc_t<64, 4>(st, ah, al, bh_, bl, p);
-    else if (BN == 128) rc = launch_conv_tc_t<128, 3>(st, ah, al, bh_, bl, p);
-    else rc = launch_conv_tc_t<256, 2>(st, ah, al, bh_, bl, p);
+    if (slabk == 32) {
+        if (BN == 64) rc = launch_conv_tc_t<64, 8, 32>(st, ah, al, bh_, bl, p);
+        else if (BN == 128) rc = launch_conv_tc_t<128, 6, 32>(st, ah, al, bh_, bl, p);
+        else rc = launch_conv_tc_t<256, 4, 32>(st, ah, al, bh_, bl, p);
+    } else {
+        if (BN == 64) rc = launch_conv_tc_t<64, 4, 64>(st, ah, al, bh_, bl, p);
+        else if (BN == 128) rc = launch_conv_tc_t<128, 3, 64>(st, ah, al, bh_, bl, p);
+        else rc = launch_conv_tc_t<256, 2, 64>(st, ah, al, bh_, bl, p);
+    }
     if (rc == 0) *launches += 1;
     return rc;
 }
