@@ -177,10 +177,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // Final epilogue of one tile for one epilogue thread (one output pixel row x kCols channels held in acc):
 // * unscale + bias, ReLU, optional fused 2x2 average pool, fp16 hi/lo split (or fp32) and the NHWC store.
 template <int kCols>
-__device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&acc)[kCols], int tile,
+__device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&acc)[kCols], int nt, int mt,
                                            int tiles_per_group, int img, int rr, int cc, int BN, int col0,
                                            const float *sbias) {
-    const int nt = tile / p.mtiles, mt = tile - nt * p.mtiles;
     const int grp = mt / tiles_per_group, rem = mt - grp * tiles_per_group;
     const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
     const int n0 = grp * p.IPT, h0 = th * p.BH, w0 = tw * p.BW;
@@ -249,7 +248,7 @@ __device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&
 //               fp32 register accumulators with round-to-nearest on the CUDA cores while the next chunk is
 //               being multiplied.  After the last chunk: * unscale + bias, ReLU, fp16 hi/lo split (or fp32)
 //               and the NHWC store.  The drain of tile i's last chunk overlaps the MMAs of tile i+1.
-template <int BN, int STAGES, int SLABK>
+template <int BN, int STAGES, int SLABK, int MT>
 __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmAh,
                                                                      const __grid_constant__ CUtensorMap tmAl,
                                                                      const __grid_constant__ CUtensorMap tmBh,
@@ -257,8 +256,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                                                                      const ConvTcParams p) {
     constexpr int kABytes = kTileM * SLABK * 2;
     constexpr int kBBytes = BN * SLABK * 2;
-    constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-    constexpr int kCols = BN / 2;  // accumulator columns owned by one epilogue thread
+    constexpr int kStageBytes = MT * 2 * kABytes + 2 * kBBytes;
+    constexpr int kAccCols = MT * BN;             // TMEM columns of one accumulator stage
+    constexpr int kCols = MT == 1 ? BN / 2 : BN;  // accumulator columns owned by one epilogue thread
+    static_assert(kAccStages * kAccCols <= 512 && kCols <= 128, "TMEM / register budget");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * kStageBytes);
@@ -271,7 +272,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_group = p.tilesW * p.tilesH;
-    const int total_tiles = p.mtiles * p.ntiles;
+    const int mgroups = (p.mtiles + MT - 1) / MT;   // work item = MT consecutive M tiles x one N tile (they share B)
+    const int total_tiles = mgroups * p.ntiles;
     const int cpt = p.Cin / SLABK;  // channel slabs per tap
     const int nslabs = 9 * cpt;
     const int nchunks = (nslabs + p.chunk_slabs - 1) / p.chunk_slabs;
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, kAccStages * BN);
+    if (warp == 1) tmem_alloc(tmem_slot, kAccStages * kAccCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -291,13 +293,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
     if (warp == 0) {
         if (lane == 0) {  // ---------------- TMA producer
             const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.IPT) * SLABK * 2;
-            const uint32_t tx_bytes = 2 * a_box_bytes + 2 * kBBytes;
+            const uint32_t tx_bytes = MT * 2 * a_box_bytes + 2 * kBBytes;
             uint32_t g = 0;  // slabs issued so far (ring position), continues across tiles
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile / p.mtiles, mt = tile - nt * p.mtiles;
-                const int grp = mt / tiles_per_group, rem = mt - grp * tiles_per_group;
-                const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
-                const int n0 = grp * p.IPT, h0 = th * p.BH, w0 = tw * p.BW;
+                const int nt = tile / mgroups, mg = tile - nt * mgroups;
+                int n0[MT], h0[MT], w0[MT];
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {  // an M tile past the end (odd tile count) lands out of bounds: zero fill
+                    const int mt = mg * MT + i;
+                    const int grp = mt / tiles_per_group, rem = mt - grp * tiles_per_group;
+                    const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+                    n0[i] = grp * p.IPT; h0[i] = th * p.BH; w0[i] = tw * p.BW;
+                }
                 for (int s = 0; s < nslabs; ++s, ++g) {
                     const uint32_t stage = g % STAGES, it = g / STAGES;
                     mbar_wait(&empty[stage], (it & 1) ^ 1);  // passes at once on the first lap
@@ -305,10 +312,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                     mbar_expect_tx(&full[stage], tx_bytes);
                     const int tap = s / cpt, c0 = (s - tap * cpt) * SLABK;
                     const int kh = tap / 3, kw = tap - kh * 3;
-                    tma_load_4d(&tmAh, &full[stage], sb, c0, w0 + kw - 1, h0 + kh - 1, n0);
-                    tma_load_4d(&tmAl, &full[stage], sb + kABytes, c0, w0 + kw - 1, h0 + kh - 1, n0);
-                    tma_load_2d(&tmBh, &full[stage], sb + 2 * kABytes, tap * p.Cin + c0, nt * BN);
-                    tma_load_2d(&tmBl, &full[stage], sb + 2 * kABytes + kBBytes, tap * p.Cin + c0, nt * BN);
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        tma_load_4d(&tmAh, &full[stage], sb + i * 2 * kABytes, c0, w0[i] + kw - 1, h0[i] + kh - 1, n0[i]);
+                        tma_load_4d(&tmAl, &full[stage], sb + i * 2 * kABytes + kABytes, c0, w0[i] + kw - 1, h0[i] + kh - 1, n0[i]);
+                    }
+                    tma_load_2d(&tmBh, &full[stage], sb + MT * 2 * kABytes, tap * p.Cin + c0, nt * BN);
+                    tma_load_2d(&tmBl, &full[stage], sb + MT * 2 * kABytes + kBBytes, tap * p.Cin + c0, nt * BN);
                 }
             }
         }
@@ -321,23 +331,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                     const uint32_t a = c % kAccStages;
                     mbar_wait(&acc_empty[a], ((c / kAccStages) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + a * BN;
+                    const uint32_t d0 = tmem_base + a * kAccCols;
                     const int s1 = min(s0 + p.chunk_slabs, nslabs);
                     for (int s = s0; s < s1; ++s, ++g) {
                         const uint32_t stage = g % STAGES, it = g / STAGES;
                         mbar_wait(&full[stage], it & 1);
                         tc_fence_after();
                         const uint32_t sb = smem_u32(smem + stage * kStageBytes);
-                        const uint64_t a_hi = make_sdesc_k<SLABK>(sb), a_lo = make_sdesc_k<SLABK>(sb + kABytes);
-                        const uint64_t b_hi = make_sdesc_k<SLABK>(sb + 2 * kABytes), b_lo = make_sdesc_k<SLABK>(sb + 2 * kABytes + kBBytes);
-                        // small terms first: they meet the accumulator while it is small
+                        const uint64_t b_hi = make_sdesc_k<SLABK>(sb + MT * 2 * kABytes);
+                        const uint64_t b_lo = make_sdesc_k<SLABK>(sb + MT * 2 * kABytes + kBBytes);
 #pragma unroll
-                        for (int k = 0; k < SLABK / 16; ++k)  // +32 B per K step of 16 inside the swizzle atom
-                            umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, idesc, (s > s0 || k > 0) ? 1u : 0u);
+                        for (int i = 0; i < MT; ++i) {
+                            const uint32_t d = d0 + i * BN;
+                            const uint64_t a_hi = make_sdesc_k<SLABK>(sb + i * 2 * kABytes);
+                            const uint64_t a_lo = make_sdesc_k<SLABK>(sb + i * 2 * kABytes + kABytes);
+                            // small terms first: they meet the accumulator while it is small
 #pragma unroll
-                        for (int k = 0; k < SLABK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                            for (int k = 0; k < SLABK / 16; ++k)  // +32 B per K step of 16 inside the swizzle atom
+                                umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, idesc, (s > s0 || k > 0) ? 1u : 0u);
 #pragma unroll
-                        for (int k = 0; k < SLABK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                            for (int k = 0; k < SLABK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+                            for (int k = 0; k < SLABK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                        }
                         umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
                     }
                     umma_commit(&acc_full[a]);  // chunk complete -> epilogue may drain it
@@ -346,7 +362,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
         }
     } else {  // ---------------- epilogue warps 2..9
         const int q = warp & 3;               // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;     // column half
+        const int half = (warp - 2) >> 2;     // MT == 1: column half; MT == 2: which of the two M tiles
         const int m = q * 32 + lane;
         const int per_img = p.BW * p.BH;
         const int img = m / per_img;
@@ -361,7 +377,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                 const uint32_t a = c % kAccStages;
                 mbar_wait(&acc_full[a], (c / kAccStages) & 1);
                 tc_fence_after();
-                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + half * kCols;
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccCols + half * kCols;
 #pragma unroll
                 for (int j0 = 0; j0 < kCols; j0 += 32) {
                     uint32_t v[32];
@@ -374,12 +390,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
             }
-            store_tile<kCols>(p, acc, tile, tiles_per_group, img, rr, cc, BN, half * kCols, sbias);
+            const int nt = tile / mgroups, mg = tile - nt * mgroups;
+            if (MT == 1) store_tile<kCols>(p, acc, nt, mg, tiles_per_group, img, rr, cc, BN, half * kCols, sbias);
+            else store_tile<kCols>(p, acc, nt, mg * MT + half, tiles_per_group, img, rr, cc, BN, 0, sbias);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, kAccStages * BN);
+    if (warp == 1) tmem_dealloc(tmem_base, kAccStages * kAccCols);
 }
 
 // ---------------------------------------------------------------- 64 -> 64 channels (block 1, conv2)
@@ -513,7 +531,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_c64_kernel(const __gr
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
             }
-            store_tile<kCols>(p, acc, tile, tiles_per_group, 0, rr, cc, BN, half * kCols, sbias);
+            store_tile<kCols>(p, acc, 0, tile, tiles_per_group, 0, rr, cc, BN, half * kCols, sbias);
         }
     }
     tc_fence_before();
@@ -660,19 +678,19 @@ int num_sms() {
     return n;
 }
 
-template <int BN, int STAGES, int SLABK>
+template <int BN, int STAGES, int SLABK, int MT = 1>
 int launch_conv_tc_t(cudaStream_t st, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh,
                      const CUtensorMap &bl, const ConvTcParams &p) {
-    constexpr int smem = STAGES * (2 * kTileM * SLABK * 2 + 2 * BN * SLABK * 2) + 1024 + 256 + 2048 * 4;  // ring, align, barriers, bias
+    constexpr int smem = STAGES * (MT * 2 * kTileM * SLABK * 2 + 2 * BN * SLABK * 2) + 1024 + 256 + 2048 * 4;  // ring, align, barriers, bias
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES, SLABK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES, SLABK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return tc_fail("cudaFuncSetAttribute", cudaGetErrorString(e));
         configured = true;
     }
-    const int total = p.mtiles * p.ntiles;
+    const int total = ((p.mtiles + MT - 1) / MT) * p.ntiles;
     const int grid = total < num_sms() ? total : num_sms();  // persistent: one CTA per SM
-    conv3x3_tc_kernel<BN, STAGES, SLABK><<<grid, kConvThreads, smem, st>>>(ah, al, bh, bl, p);
+    conv3x3_tc_kernel<BN, STAGES, SLABK, MT><<<grid, kConvThreads, smem, st>>>(ah, al, bh, bl, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tc_fail("conv3x3_tc_kernel launch", cudaGetErrorString(e));
     return 0;
@@ -709,6 +727,12 @@ int slab_k(int cin) {
     }
     if (forced) return forced;
     return cin >= 1024 ? 32 : 64;
+}
+
+bool use_mt2() {  // STITO_TC_MT2=0: one M tile per work item on the Cout = 128 layers (developer knob)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("STITO_TC_MT2"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v != 0;
 }
 
 bool use_c64() {  // STITO_TC_C64=0 falls back to the generic kernel for block 1 (developer knob)
@@ -836,6 +860,7 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, con
         else rc = launch_conv_tc_t<256, 4, 32>(st, ah, al, bh_, bl, p);
     } else {
         if (BN == 64) rc = launch_conv_tc_t<64, 4, 64>(st, ah, al, bh_, bl, p);
+        else if (BN == 128 && l.cin >= 128 && use_mt2()) rc = launch_conv_tc_t<128, 2, 64, 2>(st, ah, al, bh_, bl, p);  // 2 M tiles share B (-4.5 % on b2c2; b2c1, K = 576, prefers the deeper 3-stage ring)
         else if (BN == 128) rc = launch_conv_tc_t<128, 3, 64>(st, ah, al, bh_, bl, p);
         else rc = launch_conv_tc_t<256, 2, 64>(st, ah, al, bh_, bl, p);
     }
