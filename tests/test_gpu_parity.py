@@ -379,3 +379,75 @@ def test_run_es_smoke(models):
     assert res["wopt"].shape == (D,) and -1.0 <= res["fopt"] <= 1.0
     assert res["wopt_history"][0] is None and res["fval_history"][1] >= res["fopt"]
     assert list(res["params"]) == ["ParametricEQ"]
+
+
+# ------------------------------------------------------------------------------- C-ABI error behaviour
+def test_abi_error_codes_and_messages(models):
+    """Call-order and argument errors come back as negative STITO_E* codes with a message (never a crash)."""
+    from st_ito_b200 import _lib
+    from st_ito_b200.engine import Engine, compile_chain
+
+    ours, _ = models
+    eng = Engine(model=ours)
+    plugins, D, _ = native_plugins(["eq"])
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    W = np.random.RandomState(0).rand(3, D)
+    with pytest.raises(_lib.StitoError) as e:  # no input yet
+        eng.eval_population(W, 0, 40000)
+    assert e.value.code == -3 and "stito_set_input" in str(e.value)
+    x = test_signal(1, 40000, seed=9)
+    eng.set_input(x)
+    with pytest.raises(_lib.StitoError) as e:  # no target yet
+        eng.eval_population(W, 0, 40000)
+    assert e.value.code == -3 and "target" in str(e.value)
+    eng.set_target(x)
+    with pytest.raises(_lib.StitoError) as e:  # wrong parameter-vector length
+        eng.eval_population(W[:, :-1], 0, 40000)
+    assert e.value.code == -1 and "chain expects" in str(e.value)
+    with pytest.raises(_lib.StitoError) as e:  # view outside the (padded) input
+        eng.eval_population(W, 1000, 40000)
+    assert e.value.code == -1 and "outside" in str(e.value)
+    with pytest.raises(_lib.StitoError) as e:  # fewer than 32 frames: the encoder's five 2x2 pools would hit zero
+        eng.eval_population(W, 0, 20000)
+    assert e.value.code == -1 and "too short" in str(e.value)
+    with pytest.raises(_lib.StitoError):
+        eng.set_input(np.zeros((3, 100), dtype=np.float32))
+    with pytest.raises(_lib.StitoError):
+        eng.set_precision(7)
+    fit, _, _ = eng.eval_population(W, 0, 40000)  # the handle is still usable after the failures
+    assert fit.shape == (3,) and torch.isfinite(fit).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("L,chs", [(33001, 1), (77777, 2)])
+def test_eval_population_ragged_lengths_match_oracle(models_centred, oracle_dsp, L, chs):
+    """Odd, non-chunk-aligned lengths through every kernel (EQ chunks, compressor super-blocks, reverb
+    super-steps, STFT reflect padding, partial conv tiles) with the parallel=True length policy (no padding)."""
+    from oracle import cnn14
+    from st_ito_b200.engine import compile_chain
+
+    ours, ref = models_centred
+    eng = ours.stito_engine()
+    eng.set_precision(1)
+    kinds = ["eq", "comp", "reverb"]
+    plugins, D, _ = native_plugins(kinds)
+    oplugins, _, _ = oracle_plugins(oracle_dsp, kinds)
+    x = test_signal(chs, L, seed=300 + chs)
+    x = x / np.abs(x).max()
+    rng = np.random.RandomState(L)
+    w_star, W = rng.rand(D), rng.rand(5, D)
+    tgt = oracle_dsp.process_audio(x, w_star, SR, oplugins)
+    te = cnn14.get_param_embeds(torch.from_numpy(tgt[None].copy()), ref, SR)
+    audios = torch.stack([torch.from_numpy(oracle_dsp.process_audio(x, w, SR, oplugins)) for w in W])
+    want = cnn14.fitness(cnn14.get_param_embeds(audios, ref, SR), te).numpy()
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    eng.set_input(x)
+    eng.set_target(tgt)
+    fit, _, aud = eng.eval_population(W, 0, L, want_audio=True, in_chs=chs)
+    got = fit.numpy()
+    assert np.all(np.abs(got - want) <= 1e-4 * np.maximum(np.abs(want), 1e-3)), np.abs(got - want).max()
+    np.testing.assert_array_equal(np.argsort(got, kind="stable"), np.argsort(want, kind="stable"))
+    assert aud.shape == (5, 2, L)  # the stereo reverb up-mixes mono input (style_transfer.py:94-95)
+    assert np.abs(aud.numpy() - audios.numpy()).max() <= 1e-5
