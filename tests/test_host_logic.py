@@ -249,3 +249,32 @@ def test_run_es_population_sharding_world2_gloo(tmp_path, seed):
         assert one["fopt"] == two[0]["fopt"] and one["wopt"] == two[0]["wopt"]
         assert all(c == [10, 0, 300000] for c in one["calls"])
         assert one["fopt"] <= min(one["hist"]) and one["fopt"] < 0.5  # best-so-far of a distance-to-optimum objective
+
+
+# ------------------------------------------------------------------------- checkpoint loading (CPU only)
+def test_load_param_model_reads_a_lightning_checkpoint(tmp_path):
+    """load_param_model (reference utils.py:511-551): Lightning ckpt with `encoder.`-prefixed keys next to a
+    config.yaml whose class_path still says `lcap.models.panns.Cnn14`; other sub-modules' keys are dropped."""
+    import yaml
+
+    from st_ito_b200.models.panns import AFX_REP_ARGS, Cnn14
+    from st_ito_b200.utils import load_param_model, make_synthetic_param_model
+
+    src = make_synthetic_param_model(seed=11)
+    sd = {f"encoder.{k}": v.clone() for k, v in src.state_dict().items()}
+    sd["instance_estimator.0.weight"] = torch.zeros(4, 4)  # ParameterEstimator heads: ignored by the loader
+    sd["preset_estimator.0.bias"] = torch.zeros(4)
+    ckpt = tmp_path / "afx-rep.ckpt"
+    torch.save({"state_dict": sd, "epoch": 3}, ckpt)
+    cfg = {"model": {"class_path": "lcap.methods.param.ParameterEstimator",
+                     "init_args": {"encoder": {"class_path": "lcap.models.panns.Cnn14", "init_args": dict(AFX_REP_ARGS)}}}}
+    (tmp_path / "config.yaml").write_text(yaml.safe_dump(cfg))
+    m = load_param_model(str(ckpt))
+    assert isinstance(m, Cnn14) and not m.training
+    got = m.state_dict()
+    for k, v in src.state_dict().items():
+        assert torch.equal(got[k], v), k
+    assert got["spectrogram_extractor.stft.conv_real.weight"].shape == (1025, 1, 2048)
+    assert got["logmel_extractor.melW"].shape == (1025, 128)
+    with pytest.raises(FileNotFoundError, match="afx-rep.ckpt"):
+        load_param_model(str(tmp_path / "missing" / "afx-rep.ckpt"))
