@@ -592,8 +592,8 @@ __global__ void __launch_bounds__(NCH * 256) reverb_kernel(SigView in, const flo
 // ---------------------------------------------------------------- reverb, fast path
 // The two channels of juce::Reverb share only the mono input sum and the final wet cross-mix, so the
 // comb/all-pass network of every (candidate, channel) runs in its own CTA and a trivial element-wise
-// kernel does the mix.  Delay lines are power-of-two rings (combs 4096, all-passes 1024 floats) indexed
-// with (n - delay) & mask: no per-ring position state and no wrap-around branches.
+// kernel does the mix.  All-pass delay lines are power-of-two rings indexed with (n - delay) & mask; the comb
+// lines are 3-super-step rings with a mirrored head (see kCombRing).
 //
 // Time is cut into super-steps of S = 32*seg samples, S <= shortest comb delay, so that inside a
 // super-step every delayed read refers to samples of EARLIER super-steps:
@@ -602,13 +602,17 @@ __global__ void __launch_bounds__(NCH * 256) reverb_kernel(SigView in, const flo
 //   * 7 all-pass warps (224 threads = one sub-block <= shortest all-pass delay): sum the 8 comb outputs
 //     (= ring values of earlier super-steps, read straight from the comb rings) and run the 4 series
 //     all-passes sample-parallel, sub-block after sub-block, synchronised by a named barrier of their own.
-// The two groups do not depend on each other inside a super-step (the 4096-float comb rings keep a full
-// super-step of history beyond the longest delay, so the comb writes cannot clobber what the all-pass group
-// still has to read) and run concurrently; one __syncthreads per super-step (429 for 10 s) is the only
+// The two groups do not depend on each other inside a super-step (the comb rings keep a full super-step of
+// history beyond the longest delay, so the comb writes cannot clobber what the all-pass group still has to
+// read) and run concurrently; one __syncthreads per super-step (429 for 10 s) is the only
 // CTA-wide barrier.  The next super-step's input is prefetched into a double buffer meanwhile.
 constexpr int kRevMaxSegF = 35;          // instantiated for seg = 35 (>= 44.3 kHz: S = 1120 = 5 sub-blocks) and 32
 constexpr int kRevSub = 224;             // all-pass sub-block: <= shortest all-pass line at >= 44.1 kHz
-constexpr int kCombRing = 4096, kApRing = 1024;
+constexpr int kApRing = 1024;
+// Comb rings hold 3 super-steps (RL = 3 S >= longest delay + S) plus a mirror of the first super-step behind the
+// end, so that a lane's SEG consecutive reads / writes are one contiguous run: base pointer + immediate offsets
+// instead of an add / mask / scale per access (a third of the comb role's instructions).
+constexpr int kCombRing = 4 * 32 * kRevMaxSegF;  // per-comb allocation: 3 S + mirror S at the largest S
 constexpr int kRevCombThreads = 256, kRevThreads = kRevCombThreads + kRevSub;
 constexpr int kRevMaxS = 32 * kRevMaxSegF;
 
@@ -668,9 +672,10 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
     for (int j = 0; j < 4; ++j) ad[j] = g.ap_delay[tune][j];
     float *dst = wet + (int64_t)inst * L;
 
-    int buf = 0;
-    for (int64_t n0 = 0; n0 < L; n0 += S, buf ^= 1) {
-        const int nbase = (int)(n0 & (kCombRing * kApRing - 1));  // only the low bits matter for the masks
+    constexpr int RL = 3 * S;  // comb ring length; [RL, RL + S) mirrors [0, S)
+    int buf = 0, wbase = 0;    // wbase = ring position of this super-step's first sample: 0, S, 2S, 0, ...
+    for (int64_t n0 = 0; n0 < L; n0 += S, buf ^= 1, wbase = (wbase == 2 * S) ? 0 : wbase + S) {
+        const int nbase = (int)(n0 & (kApRing * 1024 - 1));  // only the low bits matter for the all-pass masks
         // prefetch the next super-step's input into registers now (the loads fly while this super-step is
         // computed); it is parked in the other half of the double buffer just before the barrier below
         constexpr int kPre = (kRevMaxS + kRevThreads - 1) / kRevThreads;
@@ -685,10 +690,13 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
         if (comb_role) {
             const float *inb = inbuf + buf * kRevMaxS;
             const int i0 = lane * seg;
-            const int n = nbase + i0;
+            int rb = wbase - my_delay;
+            if (rb < 0) rb += RL;
+            const float *rp = my_ring + rb + i0;   // SEG contiguous delayed samples (runs into the mirror, never wraps)
+            float *wp = my_ring + wbase + i0;
             float o[SEG];
 #pragma unroll
-            for (int i = 0; i < SEG; ++i) o[i] = my_ring[(n + i - my_delay) & (kCombRing - 1)];
+            for (int i = 0; i < SEG; ++i) o[i] = rp[i];
             float z = 0.0f;  // zero-state response of the damping one-pole over my segment
 #pragma unroll
             for (int i = 0; i < SEG; ++i) z = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(z, q.damp)));
@@ -706,17 +714,25 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
             for (int i = 0; i < SEG; ++i) {
                 sv = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(sv, q.damp)));
                 const float tv = undenorm(__fadd_rn(inb[i0 + i], __fmul_rn(sv, q.fb)));
-                my_ring[(n + i) & (kCombRing - 1)] = tv;
+                wp[i] = tv;
+                if (wbase == 0) wp[RL + i] = tv;  // keep the mirror of the ring head current
             }
             fstore = __shfl_sync(0xffffffffu, sv, 31);
         } else {
+            const float *cp[8];  // delayed comb outputs of this super-step: contiguous runs
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int rb = wbase - cd[j];
+                if (rb < 0) rb += RL;
+                cp[j] = comb + j * kCombRing + rb + a;
+            }
             for (int sb = 0; sb < nsub; ++sb) {
                 const int off = sb * kRevSub + a;
                 if (off < S) {
                     const int n = nbase + off;
                     float v = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v = __fadd_rn(v, comb[j * kCombRing + ((n - cd[j]) & (kCombRing - 1))]);
+                    for (int j = 0; j < 8; ++j) v = __fadd_rn(v, cp[j][sb * kRevSub]);
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
                         const float bv = ap[s * kApRing + ((n - ad[s]) & (kApRing - 1))];
@@ -910,7 +926,7 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
     for (int c = 0; c < 2; ++c)
         for (int j = 0; j < 8; ++j) min_comb = g.comb_size[c][j] < min_comb ? g.comb_size[c][j] : min_comb;
     const int seg = min_comb >= 32 * kRevMaxSegF ? kRevMaxSegF : 32;
-    if (wet_scratch != nullptr && min_comb >= 32 * seg && max_comb + 32 * seg <= kCombRing &&
+    if (wet_scratch != nullptr && min_comb >= 32 * seg && max_comb <= 2 * 32 * seg &&
         max_ap + kRevSub <= kApRing && min_ap >= kRevSub) {
         ReverbFastGeom fg;
         for (int c = 0; c < 2; ++c) {
