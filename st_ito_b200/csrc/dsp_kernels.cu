@@ -621,39 +621,73 @@ struct ReverbFastGeom {
     int ap_delay[2][4];
 };
 
-// inst = (p, c): stereo != 0 -> input (l + r) * 0.015, tunings of channel c; else input x_c * 0.015, left tunings
-template <int SEG>
-__global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in, const float *in_peak, float *wet,
-                                                                     int chs, int stereo, int64_t L,
-                                                                     ReverbFastGeom g, const ReverbParams *prm) {
+// inst = (p, c).  PAIR (stereo reverb on stereo audio): input (l + r) * 0.015, tunings of channel c, and the two
+// CTAs of a candidate form a thread-block cluster: every wet sample is stored into the own AND (through
+// distributed shared memory) the peer CTA's buffer, one cluster barrier per super-step replaces the CTA barrier,
+// and each CTA then mixes its own output channel  y = wet_own*wet1 + wet_peer*wet2 + x*dry  -- the wet signal never
+// touches HBM.  !PAIR: independent channels, input x_c * 0.015, left tunings, y = wet*wet1 + x*dry.
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int SEG, bool PAIR>
+__global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in, const float *in_peak, float *out,
+                                                                     int chs, int64_t L, ReverbFastGeom g,
+                                                                     const ReverbParams *prm, unsigned *out_peak) {
     extern __shared__ float sm[];
     float *comb = sm;                        // [8][kCombRing]
     float *ap = sm + 8 * kCombRing;          // [4][kApRing]
-    float *inbuf = ap + 4 * kApRing;         // [2][kRevMaxS]
+    float *inbuf = ap + 4 * kApRing;         // [3][kRevMaxS] reverb input of super-steps k-1, k, k+1 (k % 3)
+    float *xraw = inbuf + 3 * kRevMaxS;      // [3][kRevMaxS] own-channel dry input, same indexing
+    float *wetb = xraw + 3 * kRevMaxS;       // [2 (super-step parity)][2 (own, peer)][kRevMaxS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int inst = blockIdx.x;
     const int p = inst / chs, c = inst - p * chs;
-    const int tune = stereo ? c : 0;
+    const int tune = PAIR ? c : 0;
     for (int i = tid; i < 8 * kCombRing + 4 * kApRing; i += kRevThreads) sm[i] = 0.0f;
     const ReverbParams q = prm[p];
     const bool has_div = in_peak != nullptr;
     const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
     constexpr int seg = SEG, S = 32 * SEG;
     constexpr int nsub = (S + kRevSub - 1) / kRevSub;
+    constexpr int kPre = (kRevMaxS + kRevThreads - 1) / kRevThreads;
 
-    auto fetch = [&](int64_t n) -> float {
-        if (n >= L) return 0.0f;
-        if (stereo) {
-            float l = load_in(in, p, 0, n), r = load_in(in, p, 1, n);
+    // raw samples of one super-step -> (reverb input, own dry sample)
+    auto park = [&](const float (&pl)[kPre], const float (&pr)[kPre], int b) {
+        float *nin = inbuf + b * kRevMaxS, *nx = xraw + b * kRevMaxS;
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int i = tid + k * kRevThreads;
+            float l = pl[k], r = pr[k];
             if (has_div) { l = l / div; r = r / div; }
-            return __fmul_rn(__fadd_rn(l, r), 0.015f);
+            if (i < S) {
+                nin[i] = __fmul_rn(PAIR ? __fadd_rn(l, r) : l, 0.015f);
+                nx[i] = (PAIR && c == 1) ? r : l;
+            }
         }
-        float x = load_in(in, p, c, n);
-        if (has_div) x = x / div;
-        return __fmul_rn(x, 0.015f);
     };
-    for (int i = tid; i < S; i += kRevThreads) inbuf[i] = fetch(i);
-    __syncthreads();
+    auto fetch = [&](float (&pl)[kPre], float (&pr)[kPre], int64_t base) {
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int64_t n = base + tid + k * kRevThreads;
+            const bool ok = (tid + k * kRevThreads) < S && n < L;
+            pl[k] = ok ? load_in(in, p, PAIR ? 0 : c, n) : 0.0f;
+            pr[k] = (ok && PAIR) ? load_in(in, p, 1, n) : 0.0f;
+        }
+    };
+    {
+        float pl[kPre], pr[kPre];
+        fetch(pl, pr, 0);
+        park(pl, pr, 0);
+    }
+    uint32_t peer_wet = 0;  // shared::cluster address of the peer CTA's wetb
+    if (PAIR) {
+        const uint32_t local = (uint32_t)__cvta_generic_to_shared(wetb);
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_wet) : "r"(local), "r"((uint32_t)(c ^ 1)));
+        cluster_barrier();  // the peer is resident and initialised before anything is stored into it
+    } else {
+        __syncthreads();
+    }
 
     const bool comb_role = tid < kRevCombThreads;
     // comb role state
@@ -670,25 +704,33 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
     for (int j = 0; j < 8; ++j) cd[j] = g.comb_delay[tune][j];
 #pragma unroll
     for (int j = 0; j < 4; ++j) ad[j] = g.ap_delay[tune][j];
-    float *dst = wet + (int64_t)inst * L;
+    float *dst = out + (int64_t)inst * L;
+    float pk = 0.0f;
+
+    // mix of one finished super-step (both wet channels are in shared memory): y = wet_own*wet1 + wet_peer*wet2 + x*dry
+    auto mix = [&](int64_t m0, int par, int xb, int first, int nthreads) {
+        const float *wo = wetb + par * 2 * kRevMaxS, *wpeer = wo + kRevMaxS, *xr = xraw + xb * kRevMaxS;
+        const int cnt = (int)min((int64_t)S, L - m0);
+        for (int i = first; i < cnt; i += nthreads) {
+            float y;
+            if (PAIR) y = __fadd_rn(__fadd_rn(__fmul_rn(wo[i], q.wet1), __fmul_rn(wpeer[i], q.wet2)), __fmul_rn(xr[i], q.dry));
+            else y = __fadd_rn(__fmul_rn(wo[i], q.wet1), __fmul_rn(xr[i], q.dry));
+            dst[m0 + i] = y;
+            pk = fmaxf(pk, fabsf(y));
+        }
+    };
 
     constexpr int RL = 3 * S;  // comb ring length; [RL, RL + S) mirrors [0, S)
-    int buf = 0, wbase = 0;    // wbase = ring position of this super-step's first sample: 0, S, 2S, 0, ...
-    for (int64_t n0 = 0; n0 < L; n0 += S, buf ^= 1, wbase = (wbase == 2 * S) ? 0 : wbase + S) {
+    int par = 0, ib = 0, wbase = 0;  // wbase = ring position of this super-step's first sample: 0, S, 2S, 0, ...
+    for (int64_t n0 = 0; n0 < L; n0 += S, par ^= 1, ib = (ib == 2) ? 0 : ib + 1, wbase = (wbase == 2 * S) ? 0 : wbase + S) {
         const int nbase = (int)(n0 & (kApRing * 1024 - 1));  // only the low bits matter for the all-pass masks
         // prefetch the next super-step's input into registers now (the loads fly while this super-step is
-        // computed); it is parked in the other half of the double buffer just before the barrier below
-        constexpr int kPre = (kRevMaxS + kRevThreads - 1) / kRevThreads;
+        // computed); it is parked in the third input buffer before the barrier below
         float pre_l[kPre], pre_r[kPre];  // raw samples: no arithmetic before the end of the super-step
-#pragma unroll
-        for (int k = 0; k < kPre; ++k) {
-            const int64_t n = n0 + S + tid + k * kRevThreads;
-            const bool ok = (tid + k * kRevThreads) < S && n < L;
-            pre_l[k] = ok ? load_in(in, p, stereo ? 0 : c, n) : 0.0f;
-            pre_r[k] = (ok && stereo) ? load_in(in, p, 1, n) : 0.0f;
-        }
+        fetch(pre_l, pre_r, n0 + S);
+        float *wown = wetb + par * 2 * kRevMaxS;
         if (comb_role) {
-            const float *inb = inbuf + buf * kRevMaxS;
+            const float *inb = inbuf + ib * kRevMaxS;
             const int i0 = lane * seg;
             int rb = wbase - my_delay;
             if (rb < 0) rb += RL;
@@ -740,49 +782,26 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
                         ap[s * kApRing + (n & (kApRing - 1))] = tv;
                         v = __fsub_rn(bv, v);
                     }
-                    if (n0 + off < L) dst[n0 + off] = v;
+                    wown[off] = v;
+                    if (PAIR)  // the same sample into the peer CTA's "peer" half (distributed shared memory)
+                        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(peer_wet + (uint32_t)((par * 2 + 1) * kRevMaxS + off) * 4u), "f"(v) : "memory");
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kRevSub) : "memory");  // all-pass group only
             }
+            // the all-pass group has slack against the comb chains: it also mixes and writes the PREVIOUS super-step
+            if (n0 > 0) mix(n0 - S, par ^ 1, ib == 0 ? 2 : ib - 1, a, kRevSub);
         }
-        {
-            float *nxt = inbuf + (buf ^ 1) * kRevMaxS;
-#pragma unroll
-            for (int k = 0; k < kPre; ++k) {
-                const int i = tid + k * kRevThreads;
-                float l = pre_l[k], r = pre_r[k];
-                if (has_div) { l = l / div; r = r / div; }
-                if (i < S) nxt[i] = __fmul_rn(stereo ? __fadd_rn(l, r) : l, 0.015f);
-            }
-        }
-        __syncthreads();
+        park(pre_l, pre_r, ib == 2 ? 0 : ib + 1);
+        if (PAIR) cluster_barrier(); else __syncthreads();
     }
-}
-
-// l' = outl*wet1 + outr*wet2 + l*dry ; r' = outr*wet1 + outl*wet2 + r*dry   (mono: y = out*wet1 + x*dry)
-__global__ void __launch_bounds__(256) reverb_mix_kernel(SigView in, const float *in_peak, const float *wet,
-                                                         float *out, int chs, int stereo, int64_t L,
-                                                         const ReverbParams *prm, unsigned *out_peak) {
-    const int stream = blockIdx.y;
-    const int p = stream / chs, c = stream - p * chs;
-    const ReverbParams q = prm[p];
-    const bool has_div = in_peak != nullptr;
-    const float div = has_div ? clip_peak(in_peak, p) : 1.0f;
-    const float *w_own = wet + (int64_t)stream * L;
-    const float *w_other = wet + (int64_t)(p * chs + (stereo ? 1 - c : c)) * L;
-    float pk = 0.0f;
-    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.x * blockDim.x) {
-        float x = load_in(in, p, c, n);
-        if (has_div) x = x / div;
-        float y;
-        if (stereo) y = __fadd_rn(__fadd_rn(__fmul_rn(w_own[n], q.wet1), __fmul_rn(w_other[n], q.wet2)), __fmul_rn(x, q.dry));
-        else y = __fadd_rn(__fmul_rn(w_own[n], q.wet1), __fmul_rn(x, q.dry));
-        out[(int64_t)stream * L + n] = y;
-        pk = fmaxf(pk, fabsf(y));
+    {   // the last super-step is mixed by everybody
+        const int64_t nsteps = (L + S - 1) / S;
+        const int64_t m0 = (nsteps - 1) * S;
+        mix(m0, (int)((nsteps - 1) & 1), (int)((nsteps - 1) % 3), tid, kRevThreads);
     }
     if (out_peak != nullptr) {
         pk = warp_max(pk);
-        if ((threadIdx.x & 31) == 0) atomic_peak(out_peak, p, pk);
+        if (lane == 0) atomic_peak(out_peak, p, pk);
     }
 }
 
@@ -913,7 +932,7 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
                           unsigned *out_peak, float *wet_scratch, int *launches) {
     if (g.block < 32) return cudaErrorInvalidValue;  // sample rate too low for the block scheme
     cudaError_t e;
-    // fast path: power-of-two rings, one CTA per (candidate, channel) + mix kernel
+    // fast path: one CTA per (candidate, channel), L / R CTAs paired in a cluster (reverb_core_kernel)
     int max_comb = 0, max_ap = 0, min_ap = 1 << 30;
     for (int c = 0; c < 2; ++c) {
         for (int j = 0; j < 8; ++j) max_comb = g.comb_size[c][j] > max_comb ? g.comb_size[c][j] : max_comb;
@@ -926,21 +945,36 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
     for (int c = 0; c < 2; ++c)
         for (int j = 0; j < 8; ++j) min_comb = g.comb_size[c][j] < min_comb ? g.comb_size[c][j] : min_comb;
     const int seg = min_comb >= 32 * kRevMaxSegF ? kRevMaxSegF : 32;
-    if (wet_scratch != nullptr && min_comb >= 32 * seg && max_comb <= 2 * 32 * seg &&
+    (void)wet_scratch;
+    if (min_comb >= 32 * seg && max_comb <= 2 * 32 * seg &&
         max_ap + kRevSub <= kApRing && min_ap >= kRevSub) {
         ReverbFastGeom fg;
         for (int c = 0; c < 2; ++c) {
             for (int j = 0; j < 8; ++j) fg.comb_delay[c][j] = g.comb_size[c][j];
             for (int j = 0; j < 4; ++j) fg.ap_delay[c][j] = g.ap_size[c][j];
         }
-        const size_t smem = (size_t)(8 * kCombRing + 4 * kApRing + 2 * kRevMaxS) * sizeof(float);
-        auto kern = seg == kRevMaxSegF ? reverb_core_kernel<kRevMaxSegF> : reverb_core_kernel<32>;
+        const size_t smem = (size_t)(8 * kCombRing + 4 * kApRing + 10 * kRevMaxS) * sizeof(float);
+        using Kern = void (*)(SigView, const float *, float *, int, int64_t, ReverbFastGeom, const ReverbParams *, unsigned *);
+        const bool pair = stereo != 0;
+        Kern kern = pair ? (seg == kRevMaxSegF ? reverb_core_kernel<kRevMaxSegF, true> : reverb_core_kernel<32, true>)
+                         : (seg == kRevMaxSegF ? reverb_core_kernel<kRevMaxSegF, false> : reverb_core_kernel<32, false>);
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<P * chs, kRevThreads, smem, st>>>(in, in_peak, wet_scratch, chs, stereo, L, fg, prm);
-        dim3 grid(grid_for(L, 256, P * chs), P * chs);
-        reverb_mix_kernel<<<grid, 256, 0, st>>>(in, in_peak, wet_scratch, out, chs, stereo, L, prm, out_peak);
-        *launches += 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(P * chs);
+        cfg.blockDim = dim3(kRevThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;  // the L / R CTAs of a candidate exchange their wet signals
+        attr[0].val.clusterDim.x = pair ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, in, in_peak, out, chs, L, fg, prm, out_peak);
+        if (e != cudaSuccess) return e;
+        *launches += 1;
         return cudaGetLastError();
     }
     const size_t smem = (size_t)(g.total + g.block) * sizeof(float);

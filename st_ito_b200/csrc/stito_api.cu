@@ -362,9 +362,8 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
                 break;
             case STITO_FX_REVERB: {
                 const int stereo = (cur_chs == 2 && d.num_channels == 2) ? 1 : 0;
-                CU(h->wet.ensure((size_t)P * cur_chs * L * sizeof(float)));
                 cudaError_t e = launch_reverb(st, cur, in_peak, out, P, cur_chs, stereo, L, h->rgeom,
-                                              reinterpret_cast<const ReverbParams *>(slot), opk, h->wet.as<float>(), launches);
+                                              reinterpret_cast<const ReverbParams *>(slot), opk, nullptr, launches);
                 if (e == cudaErrorInvalidValue) return fail(STITO_EINVAL, "reverb: unsupported sample rate %.1f", c.sample_rate);
                 CU(e);
                 break;
