@@ -451,3 +451,32 @@ def test_eval_population_ragged_lengths_match_oracle(models_centred, oracle_dsp,
     np.testing.assert_array_equal(np.argsort(got, kind="stable"), np.argsort(want, kind="stable"))
     assert aud.shape == (5, 2, L)  # the stereo reverb up-mixes mono input (style_transfer.py:94-95)
     assert np.abs(aud.numpy() - audios.numpy()).max() <= 1e-5
+
+
+def test_run_optim_cli_end_to_end(tmp_path):
+    """scripts/run_optim.py with the reference's flags: wavs in, output wav + parameters json out."""
+    import json
+    import importlib.util
+
+    from scipy.io import wavfile
+
+    spec = importlib.util.spec_from_file_location("run_optim", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "scripts", "run_optim.py"))
+    run_optim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(run_optim)
+    x = test_signal(2, 48000, seed=11)
+    wavfile.write(tmp_path / "in.wav", SR, np.ascontiguousarray(x.T))
+    wavfile.write(tmp_path / "tgt.wav", SR, np.ascontiguousarray((0.5 * x[:, ::-1]).T.copy()))
+    res = run_optim.main([str(tmp_path / "in.wav"), str(tmp_path / "tgt.wav"), "--effect-type", "basic",
+                          "--max-iters", "2", "--popsize", "6", "--max-length", "48000", "--synthetic-weights",
+                          "--seed", "0", "--output-dir", str(tmp_path / "out")])
+    run_dir = tmp_path / "out" / "in_to_tgt_es"
+    sr, y = wavfile.read(run_dir / "output_audio_sigma=0.33.wav")
+    assert sr == SR and y.shape == (48000, 2) and abs(np.abs(y).max() - 1.0) < 1e-6
+    params = json.load(open(run_dir / "parameters_sigma=0.33.json"))
+    assert list(params) == ["ParametricEQ", "Compressor", "Distortion", "Delay", "Reverb"]
+    assert len(params["ParametricEQ"]) == 18 and "our_bypass" not in params["ParametricEQ"]  # run_optim's loader
+    assert -24.0 <= params["ParametricEQ"]["low_shelf_gain_db"] <= 24.0
+    assert res["wopt"].shape == (31,) and len(res["fval_history"]) == 2
+    with pytest.raises(ValueError, match="vst"):
+        run_optim.main([str(tmp_path / "in.wav"), str(tmp_path / "tgt.wav")])
