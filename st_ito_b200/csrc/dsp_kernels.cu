@@ -48,14 +48,23 @@ __device__ __forceinline__ float warp_max(float v) {
 // ------------------------------------------------------------------------------ EQ
 // One sample through the cascade, scipy.signal.lfilter evaluation order:
 //   y = z0 + b0*x;  z0 = (z1 + b1*x) - a1*y;  z1 = b2*x - a2*y       cf = {b0,b1,b2,a1,a2}
+template <bool EXACT = true>
 __device__ __forceinline__ double eq_step(double v, const double (&cf)[6][5], double (&z0)[6],
                                           double (&z1)[6]) {
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
-        const double y = __dadd_rn(z0[s], __dmul_rn(cf[s][0], v));
-        z0[s] = __dsub_rn(__dadd_rn(z1[s], __dmul_rn(cf[s][1], v)), __dmul_rn(cf[s][3], y));
-        z1[s] = __dsub_rn(__dmul_rn(cf[s][2], v), __dmul_rn(cf[s][4], y));
-        v = y;
+        if (EXACT) {  // lfilter's operation order, every product and sum rounded separately: bit-identical output
+            const double y = __dadd_rn(z0[s], __dmul_rn(cf[s][0], v));
+            z0[s] = __dsub_rn(__dadd_rn(z1[s], __dmul_rn(cf[s][1], v)), __dmul_rn(cf[s][3], y));
+            z1[s] = __dsub_rn(__dmul_rn(cf[s][2], v), __dmul_rn(cf[s][4], y));
+            v = y;
+        } else {      // fused multiply-adds (5 instead of 9 fp64 instructions): only for the zero-state pre-pass,
+                      // whose result seeds chunk states that are rounding-level approximations anyway
+            const double y = fma(cf[s][0], v, z0[s]);
+            z0[s] = fma(-cf[s][3], y, fma(cf[s][1], v, z1[s]));
+            z1[s] = fma(-cf[s][4], y, cf[s][2] * v);
+            v = y;
+        }
     }
     return v;
 }
@@ -102,10 +111,10 @@ __global__ void __launch_bounds__(128) eq_chunk_kernel(SigView in, const float *
                 float4 x = __ldg(reinterpret_cast<const float4 *>(src + i));
                 if (has_div) { x.x = x.x / div; x.y = x.y / div; x.z = x.z / div; x.w = x.w / div; }
                 float4 y;
-                y.x = (float)eq_step((double)x.x, cf, z0, z1);
-                y.y = (float)eq_step((double)x.y, cf, z0, z1);
-                y.z = (float)eq_step((double)x.z, cf, z0, z1);
-                y.w = (float)eq_step((double)x.w, cf, z0, z1);
+                y.x = (float)eq_step<APPLY>((double)x.x, cf, z0, z1);
+                y.y = (float)eq_step<APPLY>((double)x.y, cf, z0, z1);
+                y.z = (float)eq_step<APPLY>((double)x.z, cf, z0, z1);
+                y.w = (float)eq_step<APPLY>((double)x.w, cf, z0, z1);
                 if (APPLY) {
                     *reinterpret_cast<float4 *>(dst + i) = y;
                     pk = fmaxf(pk, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
@@ -115,7 +124,7 @@ __global__ void __launch_bounds__(128) eq_chunk_kernel(SigView in, const float *
             for (int i = 0; i < len; ++i) {
                 float x = __ldg(src + i);
                 if (has_div) x = x / div;
-                const float y = (float)eq_step((double)x, cf, z0, z1);
+                const float y = (float)eq_step<APPLY>((double)x, cf, z0, z1);
                 if (APPLY) { dst[i] = y; pk = fmaxf(pk, fabsf(y)); }
             }
         }
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(kStitchThreads) eq_stitch_kernel(int chs, int 
                 z0[s] = (lane == 2 * s) ? 1.0 : 0.0;
                 z1[s] = (lane == 2 * s + 1) ? 1.0 : 0.0;
             }
-            for (int i = 0; i < kEqChunk; ++i) (void)eq_step(0.0, cf, z0, z1);
+            for (int i = 0; i < kEqChunk; ++i) (void)eq_step<false>(0.0, cf, z0, z1);
 #pragma unroll
             for (int s = 0; s < 6; ++s) { Msm[2 * s][lane] = z0[s]; Msm[2 * s + 1][lane] = z1[s]; }
         }
