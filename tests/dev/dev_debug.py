@@ -1,6 +1,6 @@
 """Developer diagnostics: where do embedding / fitness differences vs the oracle come from?"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import contextlib, io
 import numpy as np, torch
 from oracle import cnn14, dsp

@@ -2,7 +2,7 @@
 against fp64 truth, on the golden fitness fixture (centred heads).  CPU only."""
 import os, sys
 import numpy as np, torch, torch.nn.functional as F
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import cnn14, dsp
 from tests.signals import test_signal
 

@@ -1,6 +1,6 @@
 """Developer check: tensor-core (fp16x3) encoder vs the fp32 CUDA-core mode on the same inputs."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from st_ito_b200.utils import make_synthetic_param_model
 from tests.signals import test_signal
