@@ -480,3 +480,44 @@ def test_run_optim_cli_end_to_end(tmp_path):
     assert res["wopt"].shape == (31,) and len(res["fval_history"]) == 2
     with pytest.raises(ValueError, match="vst"):
         run_optim.main([str(tmp_path / "in.wav"), str(tmp_path / "tgt.wav")])
+
+
+@pytest.mark.parametrize("sr", [44100, 32000])
+def test_reverb_and_chain_at_other_sample_rates(oracle_dsp, sr):
+    """44.1 kHz selects the 32-samples-per-lane Freeverb variant (shortest comb < 1120 samples); 32 kHz falls back
+    to the generic single-CTA kernel.  EQ / compressor constants also depend on the sample rate."""
+    from st_ito_b200.style_transfer import process_audio
+
+    kinds = ["eq", "comp", "reverb"]
+    plugins, D, _ = native_plugins(kinds)
+    oplugins, _, _ = oracle_plugins(oracle_dsp, kinds)
+    for chs in (1, 2):
+        x = test_signal(chs, 50001, seed=70 + chs)
+        w = np.random.RandomState(sr + chs).rand(D)
+        y = process_audio(x.copy(), w, sr, plugins)
+        ref = oracle_dsp.process_audio(x.copy(), w, sr, oplugins)
+        assert y.shape == ref.shape == (2, 50001)
+        assert np.abs(y - ref).max() <= 1e-5, (sr, chs, np.abs(y - ref).max())
+
+
+def test_eval_population_view_equals_cropped_input(models_centred):
+    """random_crop (style_transfer.py:505-516) evaluates a [start, start+262144) view of the resident input: same
+    fitness as uploading the cropped signal."""
+    from st_ito_b200.engine import compile_chain
+
+    ours, _ = models_centred
+    eng = ours.stito_engine()
+    eng.set_precision(1)
+    plugins, D, _ = native_plugins(["eq", "comp", "reverb"])
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    x = test_signal(2, 300000, seed=8)
+    x = x / np.abs(x).max()
+    W = np.random.RandomState(3).rand(4, D)
+    start, length = 17001, 262144
+    eng.set_input(x)
+    eng.set_target(x[:, :100000])
+    f_view, _, _ = eng.eval_population(W, start, length)
+    eng.set_input(np.ascontiguousarray(x[:, start:start + length]))
+    f_crop, _, _ = eng.eval_population(W, 0, length)
+    np.testing.assert_allclose(f_view.numpy(), f_crop.numpy(), rtol=0, atol=1e-6)
