@@ -162,6 +162,9 @@ struct ConvTcParams {
     int mtiles, ntiles;       // tile grid; the persistent CTAs walk tile = m + mtiles * n
     int chunk_slabs;          // K-slabs accumulated inside TMEM before the fp32 drain (see below)
     int pool;                 // 1: fuse the block's 2x2 average pool into the epilogue (output [N][H/2][W/2][Cout])
+    // GEMM mode (Winograd): 16 independent products M_x[Tp, Cout] = V_x[Tp, Cin] * U_x[Cout, Cin]^T; A / B are 2-D maps
+    // over [16 * Tp][Cin] and [16 * Cout][Cin]; the raw fp32 accumulators go to out_f32[(x * Tp + row) * Cout + col]
+    int gemm, gemm_Tp;
 };
 
 constexpr int kTileM = 128;
@@ -268,14 +271,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
     uint64_t *acc_empty = acc_full + kAccStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + kAccStages);
     float *sbias = reinterpret_cast<float *>(smem + STAGES * kStageBytes + 256);  // [Cout] (<= 2048 floats)
-    for (int i = threadIdx.x; i < p.Cout; i += kConvThreads) sbias[i] = __ldg(p.bias + i);
+    if (!p.gemm)
+        for (int i = threadIdx.x; i < p.Cout; i += kConvThreads) sbias[i] = __ldg(p.bias + i);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_group = p.tilesW * p.tilesH;
     const int mgroups = (p.mtiles + MT - 1) / MT;   // work item = MT consecutive M tiles x one N tile (they share B)
-    const int total_tiles = mgroups * p.ntiles;
+    const int total_tiles = mgroups * p.ntiles * (p.gemm ? 16 : 1);
     const int cpt = p.Cin / SLABK;  // channel slabs per tap
-    const int nslabs = 9 * cpt;
+    const int nslabs = (p.gemm ? 1 : 9) * cpt;
     const int nchunks = (nslabs + p.chunk_slabs - 1) / p.chunk_slabs;
 
     if (warp == 0 && lane == 0) {
@@ -296,6 +300,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
             const uint32_t tx_bytes = MT * 2 * a_box_bytes + 2 * kBBytes;
             uint32_t g = 0;  // slabs issued so far (ring position), continues across tiles
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                if (p.gemm) {  // work item = (x, nt, mt), mt fastest
+                    const int per_x = mgroups * p.ntiles;
+                    const int xi = tile / per_x, r2 = tile - xi * per_x;
+                    const int nt = r2 / mgroups, mt = r2 - nt * mgroups;
+                    for (int s = 0; s < nslabs; ++s, ++g) {
+                        const uint32_t stage = g % STAGES, it = g / STAGES;
+                        mbar_wait(&empty[stage], (it & 1) ^ 1);
+                        uint8_t *sb = smem + stage * kStageBytes;
+                        mbar_expect_tx(&full[stage], 2 * kABytes + 2 * kBBytes);
+                        tma_load_2d(&tmAh, &full[stage], sb, s * SLABK, xi * p.gemm_Tp + mt * kTileM);
+                        tma_load_2d(&tmAl, &full[stage], sb + kABytes, s * SLABK, xi * p.gemm_Tp + mt * kTileM);
+                        tma_load_2d(&tmBh, &full[stage], sb + MT * 2 * kABytes, s * SLABK, xi * p.Cout + nt * BN);
+                        tma_load_2d(&tmBl, &full[stage], sb + MT * 2 * kABytes + kBBytes, s * SLABK, xi * p.Cout + nt * BN);
+                    }
+                    continue;
+                }
                 const int nt = tile / mgroups, mg = tile - nt * mgroups;
                 int n0[MT], h0[MT], w0[MT];
 #pragma unroll
@@ -389,6 +409,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
+            }
+            if (p.gemm) {  // raw accumulators of M_x: row = my TMEM lane, kCols consecutive columns
+                const int per_x = mgroups * p.ntiles;
+                const int xi = tile / per_x, r2 = tile - xi * per_x;
+                const int gnt = r2 / mgroups, gmt = r2 - gnt * mgroups;
+                float4 *dst = reinterpret_cast<float4 *>(
+                    p.out_f32 + ((int64_t)xi * p.gemm_Tp + gmt * kTileM + m) * p.Cout + gnt * BN + half * kCols);
+#pragma unroll
+                for (int j = 0; j < kCols / 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                continue;
             }
             const int nt = tile / mgroups, mg = tile - nt * mgroups;
             if (MT == 1) store_tile<kCols>(p, acc, nt, mg, tiles_per_group, img, rr, cc, BN, half * kCols, sbias);
@@ -537,6 +567,146 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_c64_kernel(const __gr
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, kAccStages * kAccCols);
+}
+
+// ---------------------------------------------------------------- Winograd F(2x2, 3x3) for the deep layers
+// Y = A^T [ (G g G^T) . (B^T d B) ] A turns the 3x3 convolution of a 4x4 input tile d (stride 2) into 16 independent
+// channel contractions -- 16 GEMMs  M_x[tiles, Cout] = V_x[tiles, Cin] U_x[Cout, Cin]^T  with 4/9 of the direct
+// convolution's MACs.  The price is a 4x larger transformed activation (V) and an fp32 M round trip, so it pays only
+// where the activations are small next to the weights: Cin >= 1024 (b5c2, b6c1, b6c2).  V and U are split into fp16
+// hi/lo pairs like every other operand and the GEMMs run in conv3x3_tc_kernel's GEMM mode (same fp16x3 MMAs, same
+// chunked fp32 accumulation); CPU emulation of this exact scheme: 4.5e-6 relative embedding error on the
+// centred-head fixture (tests/dev/dev_emulate_winograd.py).
+// Layers with at least this many input channels use the Winograd path.  Saved MACs and transform traffic both scale with
+// the pixel count, so the break-even depends on Cin*Cout/(Cin+Cout) only; measured on B200 (P = 64): 512->512 +20 %,
+// 512->1024 +-0 %, 1024->1024 -15 %, 1024->2048 -33 %, 2048->2048 -43 %.
+constexpr int kWinoMinCin = 1024;
+constexpr float kWinoVScale = 0.25f;  // V is stored as B^T (64 d) B / 4 = 16 (B^T d B): head-room for the 4-term sums
+
+// in (hi, lo) NHWC [N][H][W][C] (values * 64) -> V (hi, lo) [16][Tp][C] (values * 16); thread = (tile, channel pair)
+__global__ void __launch_bounds__(256) wino_in_kernel(const __half *__restrict__ in_hi, const __half *__restrict__ in_lo,
+                                                      __half *__restrict__ v_hi, __half *__restrict__ v_lo, int N, int H,
+                                                      int W, int C, int th, int tw, int Tp) {
+    const int C2 = C >> 1;
+    const int64_t total = (int64_t)N * th * tw * C2;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c2 = (int)(idx % C2);
+        const int tile = (int)(idx / C2);
+        const int tx = tile % tw, ty = (tile / tw) % th, n = tile / (tw * th);
+        float d0[4][4], d1[4][4];  // the two channels of the pair
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int hh = 2 * ty - 1 + i, ww = 2 * tx - 1 + j;
+                float a = 0.f, b = 0.f;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                    const size_t o = (((size_t)n * H + hh) * W + ww) * C + 2 * c2;
+                    const __half2 h = *reinterpret_cast<const __half2 *>(in_hi + o);
+                    const __half2 l = *reinterpret_cast<const __half2 *>(in_lo + o);
+                    a = __low2float(h) + __low2float(l);
+                    b = __high2float(h) + __high2float(l);
+                }
+                d0[i][j] = a; d1[i][j] = b;
+            }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            float (&d)[4][4] = ch ? d1 : d0;
+            float t[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // B^T d
+                t[0][j] = d[0][j] - d[2][j];
+                t[1][j] = d[1][j] + d[2][j];
+                t[2][j] = d[2][j] - d[1][j];
+                t[3][j] = d[1][j] - d[3][j];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {  // (.) B
+                d[i][0] = (t[i][0] - t[i][2]) * kWinoVScale;
+                d[i][1] = (t[i][1] + t[i][2]) * kWinoVScale;
+                d[i][2] = (t[i][2] - t[i][1]) * kWinoVScale;
+                d[i][3] = (t[i][1] - t[i][3]) * kWinoVScale;
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+            const float a = d0[x >> 2][x & 3], b = d1[x >> 2][x & 3];
+            const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+            const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+            const size_t o = ((size_t)x * Tp + tile) * C + 2 * c2;
+            *reinterpret_cast<__half2 *>(v_hi + o) = __halves2half2(ha, hb);
+            *reinterpret_cast<__half2 *>(v_lo + o) = __halves2half2(la, lb);
+        }
+    }
+}
+
+// M [16][Tp][Cout] fp32 (raw accumulators) -> A^T M A * unscale + bias -> ReLU -> (2x2 average pool: exactly one
+// output tile) -> fp16 hi/lo NHWC (values * 64) or fp32 NHWC; thread = (tile, channel pair)
+__global__ void __launch_bounds__(256) wino_out_kernel(const float *__restrict__ M, const float *__restrict__ bias,
+                                                       float unscale, __half *__restrict__ out_hi,
+                                                       __half *__restrict__ out_lo, float *__restrict__ out_f32, int N,
+                                                       int H, int W, int Cout, int th, int tw, int Tp, int pool) {
+    const int C2 = Cout >> 1;
+    const int64_t total = (int64_t)N * th * tw * C2;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c2 = (int)(idx % C2);
+        const int tile = (int)(idx / C2);
+        const int tx = tile % tw, ty = (tile / tw) % th, n = tile / (tw * th);
+        float2 m[4][4];
+#pragma unroll
+        for (int x = 0; x < 16; ++x)
+            m[x >> 2][x & 3] = __ldg(reinterpret_cast<const float2 *>(M + ((size_t)x * Tp + tile) * Cout + 2 * c2));
+        const float2 bv = __ldg(reinterpret_cast<const float2 *>(bias + 2 * c2));
+        float y[2][2][2];  // [row][col][channel]
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            float t[2][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // A^T m
+                const float m0 = ch ? m[0][j].y : m[0][j].x, m1 = ch ? m[1][j].y : m[1][j].x;
+                const float m2 = ch ? m[2][j].y : m[2][j].x, m3 = ch ? m[3][j].y : m[3][j].x;
+                t[0][j] = (m0 + m1) + m2;
+                t[1][j] = (m1 - m2) - m3;
+            }
+            const float b = ch ? bv.y : bv.x;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {  // (.) A, then unscale + bias + ReLU
+                y[i][0][ch] = fmaxf(fmaf((t[i][0] + t[i][1]) + t[i][2], unscale, b), 0.0f);
+                y[i][1][ch] = fmaxf(fmaf((t[i][1] - t[i][2]) - t[i][3], unscale, b), 0.0f);
+            }
+        }
+        if (pool) {
+            const int Ho = H >> 1, Wo = W >> 1;
+            if (ty >= Ho || tx >= Wo) continue;
+            float o[2];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+                o[ch] = ((y[0][0][ch] + y[0][1][ch]) + (y[1][0][ch] + y[1][1][ch])) * (0.25f * kActScale);
+            const size_t oo = (((size_t)n * Ho + ty) * Wo + tx) * Cout + 2 * c2;
+            const __half h0 = __float2half_rn(o[0]), h1 = __float2half_rn(o[1]);
+            *reinterpret_cast<__half2 *>(out_hi + oo) = __halves2half2(h0, h1);
+            *reinterpret_cast<__half2 *>(out_lo + oo) = __halves2half2(__float2half_rn(o[0] - __half2float(h0)),
+                                                                      __float2half_rn(o[1] - __half2float(h1)));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int hh = 2 * ty + i, ww = 2 * tx + j;
+                    if (hh >= H || ww >= W) continue;
+                    const size_t oo = (((size_t)n * H + hh) * W + ww) * Cout + 2 * c2;
+                    if (out_f32 != nullptr) {
+                        *reinterpret_cast<float2 *>(out_f32 + oo) = make_float2(y[i][j][0], y[i][j][1]);
+                    } else {
+                        const float a = y[i][j][0] * kActScale, b = y[i][j][1] * kActScale;
+                        const __half h0 = __float2half_rn(a), h1 = __float2half_rn(b);
+                        *reinterpret_cast<__half2 *>(out_hi + oo) = __halves2half2(h0, h1);
+                        *reinterpret_cast<__half2 *>(out_lo + oo) = __halves2half2(__float2half_rn(a - __half2float(h0)),
+                                                                                  __float2half_rn(b - __half2float(h1)));
+                    }
+                }
+        }
+    }
 }
 
 // ------------------------------------------------------------ SIMT helpers of the fp16x3 path
@@ -688,7 +858,7 @@ int launch_conv_tc_t(cudaStream_t st, const CUtensorMap &ah, const CUtensorMap &
         if (e != cudaSuccess) return tc_fail("cudaFuncSetAttribute", cudaGetErrorString(e));
         configured = true;
     }
-    const int total = ((p.mtiles + MT - 1) / MT) * p.ntiles;
+    const int total = ((p.mtiles + MT - 1) / MT) * p.ntiles * (p.gemm ? 16 : 1);
     const int grid = total < num_sms() ? total : num_sms();  // persistent: one CTA per SM
     conv3x3_tc_kernel<BN, STAGES, SLABK, MT><<<grid, kConvThreads, smem, st>>>(ah, al, bh, bl, p);
     cudaError_t e = cudaGetLastError();
@@ -732,6 +902,12 @@ int slab_k(int cin) {
 bool use_mt2() {  // STITO_TC_MT2=0: one M tile per work item on the Cout = 128 layers (developer knob)
     static int v = -1;
     if (v < 0) { const char *e = getenv("STITO_TC_MT2"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v != 0;
+}
+
+bool use_wino() {  // STITO_TC_WINOGRAD=0: direct implicit-GEMM convolution on every layer (developer knob)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("STITO_TC_WINOGRAD"); v = (e && atoi(e) == 0) ? 0 : 1; }
     return v != 0;
 }
 
@@ -786,11 +962,57 @@ int tc_prepare_layer(const float *wf, int cin, int cout, ConvLayer *cl, std::vec
     cl->w_hi = dh;
     cl->w_lo = dl;
     cl->w_unscale = std::ldexp(1.0f, -shift);
+    if (cin < kWinoMinCin) return 0;
+
+    // Winograd-domain weights U = G g G^T, [16][cout][cin], computed in double from the BN-folded fp32 weights
+    static const double G[4][3] = {{1, 0, 0}, {0.5, 0.5, 0.5}, {0.5, -0.5, 0.5}, {0, 0, 1}};
+    const size_t nu = (size_t)16 * cout * cin;
+    std::vector<float> U(nu);
+    double umx = 0.0;
+    for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci) {
+            double g[3][3], t[4][3];
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) g[a][b] = wf[((size_t)(a * 3 + b) * cin + ci) * cout + co];
+            for (int x = 0; x < 4; ++x)
+                for (int b = 0; b < 3; ++b) t[x][b] = G[x][0] * g[0][b] + G[x][1] * g[1][b] + G[x][2] * g[2][b];
+            for (int x = 0; x < 4; ++x)
+                for (int y = 0; y < 4; ++y) {
+                    const double u = t[x][0] * G[y][0] + t[x][1] * G[y][1] + t[x][2] * G[y][2];
+                    U[((size_t)(x * 4 + y) * cout + co) * cin + ci] = (float)u;
+                    umx = std::fmax(umx, std::fabs(u));
+                }
+        }
+    int ushift = 0;
+    if (umx > 0) ushift = -(int)std::ceil(std::log2(umx));
+    if (ushift > 14) ushift = 14;
+    if (ushift < -14) ushift = -14;
+    const float uscale = std::ldexp(1.0f, ushift);
+    std::vector<__half> uh(nu), ul(nu);
+    for (size_t i = 0; i < nu; ++i) {
+        const float v = U[i] * uscale;
+        const __half h = __float2half_rn(v);
+        uh[i] = h;
+        ul[i] = __float2half_rn(v - __half2float(h));
+    }
+    void *duh = nullptr, *dul = nullptr;
+    e = cudaMalloc(&duh, nu * sizeof(__half));
+    if (e != cudaSuccess) return tc_fail("cudaMalloc(winograd weights)", cudaGetErrorString(e));
+    owned->push_back(duh);
+    e = cudaMalloc(&dul, nu * sizeof(__half));
+    if (e != cudaSuccess) return tc_fail("cudaMalloc(winograd weights)", cudaGetErrorString(e));
+    owned->push_back(dul);
+    e = cudaMemcpy(duh, uh.data(), nu * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dul, ul.data(), nu * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return tc_fail("cudaMemcpy(winograd weights)", cudaGetErrorString(e));
+    cl->u_hi = duh;
+    cl->u_lo = dul;
+    cl->u_unscale = std::ldexp(1.0f, -ushift);
     return 0;
 }
 
 void tc_workspace_release(TcWorkspace *ws) {
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TcWorkspace::kBufs; ++i) {
         if (ws->buf[i]) cudaFree(ws->buf[i]);
         ws->buf[i] = nullptr;
         ws->cap[i] = 0;
@@ -868,6 +1090,45 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, con
     return rc;
 }
 
+// One deep conv layer through Winograd F(2x2,3x3): input transform -> 16 GEMMs (conv3x3_tc_kernel, GEMM mode) ->
+// output transform (+ bias, ReLU, optional 2x2 pool, hi/lo split or fp32).
+static int conv_wino(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, const __half *in_hi, const __half *in_lo,
+                     __half *out_hi, __half *out_lo, float *out_f32, int N, int H, int W, bool pool, int *launches) {
+    const int th = (H + 1) / 2, tw = (W + 1) / 2;
+    const int T = N * th * tw;
+    const int Tp = (T + kTileM - 1) / kTileM * kTileM;
+    if (ws_ensure(ws, 4, (size_t)16 * Tp * l.cin * sizeof(__half))) return -1;
+    if (ws_ensure(ws, 5, (size_t)16 * Tp * l.cin * sizeof(__half))) return -1;
+    if (ws_ensure(ws, 6, (size_t)16 * Tp * l.cout * sizeof(float))) return -1;
+    __half *v_hi = (__half *)ws.buf[4], *v_lo = (__half *)ws.buf[5];
+    float *M = (float *)ws.buf[6];
+    wino_in_kernel<<<blocks_for((int64_t)T * (l.cin / 2), 256), 256, 0, st>>>(in_hi, in_lo, v_hi, v_lo, N, H, W, l.cin, th, tw, Tp);
+    ConvTcParams p{};
+    p.N = N; p.H = H; p.W = W; p.Cin = l.cin; p.Cout = l.cout;
+    p.BW = 16; p.BH = 8; p.IPT = 1; p.tilesW = 1; p.tilesH = 1;  // unused in GEMM mode
+    p.mtiles = Tp / kTileM;
+    p.ntiles = l.cout / 256;
+    p.gemm = 1; p.gemm_Tp = Tp;
+    p.out_f32 = M;
+    p.unscale = 1.0f; p.out_scale = 1.0f;
+    const int slabk = slab_k(l.cin);
+    p.chunk_slabs = chunk_slabs() * (64 / slabk);
+    CUtensorMap ah, al, bh_, bl;
+    if (make_w_map(&ah, v_hi, 16 * Tp, l.cin, kTileM, slabk)) return -1;   // V as [16 * Tp][Cin], box (K slab, 128 rows)
+    if (make_w_map(&al, v_lo, 16 * Tp, l.cin, kTileM, slabk)) return -1;
+    if (make_w_map(&bh_, l.u_hi, 16 * l.cout, l.cin, 256, slabk)) return -1;
+    if (make_w_map(&bl, l.u_lo, 16 * l.cout, l.cin, 256, slabk)) return -1;
+    int rc = slabk == 32 ? launch_conv_tc_t<256, 4, 32>(st, ah, al, bh_, bl, p) : launch_conv_tc_t<256, 2, 64>(st, ah, al, bh_, bl, p);
+    if (rc) return rc;
+    const float unscale = l.u_unscale / (kActScale * kWinoVScale);
+    wino_out_kernel<<<blocks_for((int64_t)T * (l.cout / 2), 256), 256, 0, st>>>(M, l.bias, unscale, out_hi, out_lo, out_f32, N, H, W,
+                                                                                  l.cout, th, tw, Tp, pool ? 1 : 0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return tc_fail("winograd transform launch", cudaGetErrorString(e));
+    *launches += 3;
+    return 0;
+}
+
 int tc_encoder_forward(cudaStream_t st, const EncoderDev &enc, TcWorkspace &ws, const float *feat, int N, int T,
                        int mel, float *pooled, int *launches, cudaEvent_t *ev) {
     // workspace: [0],[1] = hi/lo block inputs (pooled), [2] = hi+lo conv1 outputs, [3] = fp32 output of block 6
@@ -889,15 +1150,22 @@ int tc_encoder_forward(cudaStream_t st, const EncoderDev &enc, TcWorkspace &ws, 
             tc_conv_first_kernel<<<blocks_for((int64_t)px * 8 / kC1Px, 256), 256, 0, st>>>(feat, l1.w, l1.bias, m_hi, m_lo, N, H, W);
             *launches += 1;
         } else {
-            if (conv_tc(st, l1, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
+            if (l1.u_hi != nullptr && use_wino()) {
+                if (conv_wino(st, l1, ws, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
+            } else if (conv_tc(st, l1, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
         }
         if (ev) cudaEventRecord(ev[2 * b + 1], st);
+        const bool wino2 = l2.u_hi != nullptr && use_wino();
         if (b < 5) {  // conv2 + ReLU + 2x2 average pool + hi/lo split in one kernel -> next block's input
-            if (conv_tc(st, l2, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
+            if (wino2) {
+                if (conv_wino(st, l2, ws, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
+            } else if (conv_tc(st, l2, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
             H /= 2;
             W /= 2;
         } else {
-            if (conv_tc(st, l2, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, false, launches)) return -1;
+            if (wino2) {
+                if (conv_wino(st, l2, ws, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, false, launches)) return -1;
+            } else if (conv_tc(st, l2, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, false, launches)) return -1;
         }
     }
     if (ev) cudaEventRecord(ev[12], st);

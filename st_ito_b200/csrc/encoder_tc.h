@@ -9,8 +9,9 @@
 namespace stito {
 
 struct TcWorkspace {
-    void *buf[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t cap[4] = {0, 0, 0, 0};
+    static constexpr int kBufs = 7;  // 0-3: activations (see tc_encoder_forward), 4-6: Winograd V_hi, V_lo, M
+    void *buf[kBufs] = {};
+    size_t cap[kBufs] = {};
 };
 
 // true when the tcgen05 encoder is compiled in and enabled

@@ -85,6 +85,9 @@ struct ConvLayer {
     // tensor-core operands (encoder_tc.cu): fp16 hi/lo split of w * 2^shift, [cout][9*cin] K-major
     void *w_hi, *w_lo;
     float w_unscale;  // 2^-shift
+    // Winograd F(2x2,3x3) operands (deep layers only): fp16 hi/lo split of (G g G^T) * 2^shift, [16][cout][cin]
+    void *u_hi = nullptr, *u_lo = nullptr;
+    float u_unscale = 1.0f;
 };
 struct EncoderDev {
     ConvLayer conv[12];
