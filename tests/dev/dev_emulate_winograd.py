@@ -17,9 +17,18 @@ aud = torch.stack([torch.from_numpy(dsp.process_audio(x, w, SR, plugins)) for w 
 with torch.no_grad():
     feats = ref.logmel(aud)
 
-BT = torch.tensor([[1, 0, -1, 0], [0, 1, 1, 0], [0, -1, 1, 0], [0, 1, 0, -1]], dtype=torch.float64)
-G = torch.tensor([[1, 0, 0], [.5, .5, .5], [.5, -.5, .5], [0, 0, 1]], dtype=torch.float64)
-AT = torch.tensor([[1, 1, 1, 0], [0, 1, -1, -1]], dtype=torch.float64)
+F4 = len(sys.argv) > 1 and sys.argv[1] == "f4"
+if F4:   # F(4x4, 3x3)
+    BT = torch.tensor([[4, 0, -5, 0, 1, 0], [0, -4, -4, 1, 1, 0], [0, 4, -4, -1, 1, 0], [0, -2, -1, 2, 1, 0],
+                       [0, 2, -1, -2, 1, 0], [0, 4, 0, -5, 0, 1]], dtype=torch.float64)
+    G = torch.tensor([[1 / 4, 0, 0], [-1 / 6, -1 / 6, -1 / 6], [-1 / 6, 1 / 6, -1 / 6], [1 / 24, 1 / 12, 1 / 6],
+                      [1 / 24, -1 / 12, 1 / 6], [0, 0, 1]], dtype=torch.float64)
+    AT = torch.tensor([[1, 1, 1, 1, 1, 0], [0, 1, -1, 2, -2, 0], [0, 1, 1, 4, 4, 0], [0, 1, -1, 8, -8, 1]], dtype=torch.float64)
+else:    # F(2x2, 3x3)
+    BT = torch.tensor([[1, 0, -1, 0], [0, 1, 1, 0], [0, -1, 1, 0], [0, 1, 0, -1]], dtype=torch.float64)
+    G = torch.tensor([[1, 0, 0], [.5, .5, .5], [.5, -.5, .5], [0, 0, 1]], dtype=torch.float64)
+    AT = torch.tensor([[1, 1, 1, 0], [0, 1, -1, -1]], dtype=torch.float64)
+OT = AT.shape[0]; IT = BT.shape[0]
 
 def split(t, scale):
     v = (t * scale).float(); hi = v.half().float(); lo = (v - hi).half().float()
@@ -28,9 +37,9 @@ def split(t, scale):
 def winograd_conv(xin, w, mode):
     """xin [N,C,H,W] float64 (values as stored: fp32-exact), w [Co,Ci,3,3] fp32. Returns conv (pad 1) fp64."""
     N, C, H, W = xin.shape
-    Hp, Wp = (H + 1) // 2 * 2, (W + 1) // 2 * 2
+    Hp, Wp = (H + OT - 1) // OT * OT, (W + OT - 1) // OT * OT
     xp = F.pad(xin, (1, 1 + Wp - W, 1, 1 + Hp - H))
-    tiles = xp.unfold(2, 4, 2).unfold(3, 4, 2)            # [N,C,th,tw,4,4]
+    tiles = xp.unfold(2, IT, OT).unfold(3, IT, OT)        # [N,C,th,tw,IT,IT]
     V = torch.einsum("ij,nctujk,lk->nctuil", BT, tiles.double(), BT)   # B^T d B
     U = torch.einsum("ij,ocjk,lk->ocil", G, w.double(), G)             # G g G^T  [Co,Ci,4,4]
     if mode == "exact":
@@ -38,7 +47,7 @@ def winograd_conv(xin, w, mode):
     else:
         V32 = V.float()                                   # transform done in fp32 on CUDA cores
         U32 = U.float()
-        sV = 64.0
+        sV = 64.0 / (V32.abs().max().item() / xin.abs().max().item() if F4 else 1.0) if False else 64.0 / (16.0 if F4 else 1.0)
         mx = U32.abs().max().item(); shift = -int(np.ceil(np.log2(mx)))
         vh, vl = split(V32, sV); uh, ul = split(U32, 2.0 ** shift)
         M = torch.einsum("nctuil,ocil->notuil", vh, uh) + (torch.einsum("nctuil,ocil->notuil", vl, uh) + torch.einsum("nctuil,ocil->notuil", vh, ul))
@@ -71,7 +80,7 @@ def body(feats, wino_from, mode):
 rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
 with torch.no_grad():
     truth = body(feats, 99, "truth")
-    for wf in (8, 6, 2):
+    for wf in ((9,) if F4 else (8, 6, 2)):
         for mode in ("exact", "x3"):
             r = body(feats, wf, mode)
             print(f"winograd from layer {wf:2d} mode {mode:5s}: mid {rel(r[0], truth[0]):.3e} side {rel(r[1], truth[1]):.3e}")
