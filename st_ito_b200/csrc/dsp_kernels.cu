@@ -636,9 +636,10 @@ struct ReverbFastGeom {
 
 // inst = (p, c).  PAIR (stereo reverb on stereo audio): input (l + r) * 0.015, tunings of channel c, and the two
 // CTAs of a candidate form a thread-block cluster: every wet sample is stored into the own AND (through
-// distributed shared memory) the peer CTA's buffer, one cluster barrier per super-step replaces the CTA barrier,
-// and each CTA then mixes its own output channel  y = wet_own*wet1 + wet_peer*wet2 + x*dry  -- the wet signal never
-// touches HBM.  !PAIR: independent channels, input x_c * 0.015, left tunings, y = wet*wet1 + x*dry.
+// distributed shared memory) the peer CTA's buffer, followed by a release-arrive on an mbarrier in the peer CTA; the
+// peer's all-pass group acquires it at the start of the next super-step and mixes its own output channel
+// y = wet_own*wet1 + wet_peer*wet2 + x*dry  -- the wet signal never touches HBM, and the per-super-step barrier stays a
+// plain CTA barrier (a full cluster barrier with release/acquire semantics cost ~30 % of the kernel in fence stalls).  !PAIR: independent channels, input x_c * 0.015, left tunings, y = wet*wet1 + x*dry.
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -653,6 +654,9 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
     float *inbuf = ap + 4 * kApRing;         // [3][kRevMaxS] reverb input of super-steps k-1, k, k+1 (k % 3)
     float *xraw = inbuf + 3 * kRevMaxS;      // [3][kRevMaxS] own-channel dry input, same indexing
     float *wetb = xraw + 3 * kRevMaxS;       // [2 (super-step parity)][2 (own, peer)][kRevMaxS]
+    // PAIR: "the peer's wet samples of super-step k have landed": two mbarriers, k & 1 selects, phase parity (k >> 1) & 1.
+    // (With a single barrier the peer could complete phase k+1 before a delayed thread here has waited on phase k.)
+    uint64_t *xbar = reinterpret_cast<uint64_t *>(wetb + 4 * kRevMaxS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int inst = blockIdx.x;
     const int p = inst / chs, c = inst - p * chs;
@@ -693,10 +697,17 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
         fetch(pl, pr, 0);
         park(pl, pr, 0);
     }
-    uint32_t peer_wet = 0;  // shared::cluster address of the peer CTA's wetb
+    uint32_t peer_wet = 0, peer_bar = 0;  // shared::cluster addresses of the peer CTA's wetb / xbar
     if (PAIR) {
         const uint32_t local = (uint32_t)__cvta_generic_to_shared(wetb);
+        const uint32_t lbar = (uint32_t)__cvta_generic_to_shared(xbar);
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_wet) : "r"(local), "r"((uint32_t)(c ^ 1)));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_bar) : "r"(lbar), "r"((uint32_t)(c ^ 1)));
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lbar), "r"((uint32_t)kRevSub));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lbar + 8), "r"((uint32_t)kRevSub));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
         cluster_barrier();  // the peer is resident and initialised before anything is stored into it
     } else {
         __syncthreads();
@@ -735,7 +746,8 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
 
     constexpr int RL = 3 * S;  // comb ring length; [RL, RL + S) mirrors [0, S)
     int par = 0, ib = 0, wbase = 0;  // wbase = ring position of this super-step's first sample: 0, S, 2S, 0, ...
-    for (int64_t n0 = 0; n0 < L; n0 += S, par ^= 1, ib = (ib == 2) ? 0 : ib + 1, wbase = (wbase == 2 * S) ? 0 : wbase + S) {
+    int step = 0;
+    for (int64_t n0 = 0; n0 < L; n0 += S, ++step, par ^= 1, ib = (ib == 2) ? 0 : ib + 1, wbase = (wbase == 2 * S) ? 0 : wbase + S) {
         const int nbase = (int)(n0 & (kApRing * 1024 - 1));  // only the low bits matter for the all-pass masks
         // prefetch the next super-step's input into registers now (the loads fly while this super-step is
         // computed); it is parked in the third input buffer before the barrier below
@@ -774,6 +786,21 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
             }
             fstore = __shfl_sync(0xffffffffu, sv, 31);
         } else {
+            // the all-pass group has slack against the comb chains: it also mixes and writes the PREVIOUS super-step.
+            // First thing in the super-step, so that its global stores have drained long before the release fence of
+            // the cluster barrier below (issued right before the barrier they cost ~30 % of the kernel in fence stalls).
+            if (n0 > 0) {
+                if (PAIR) {  // the peer's wet samples of the previous super-step have landed in my wetb (acquire)
+                    const uint32_t lbar = (uint32_t)__cvta_generic_to_shared(xbar) + 8u * (uint32_t)((step - 1) & 1);
+                    const uint32_t parity = (uint32_t)(((step - 1) >> 1) & 1);
+                    uint32_t ok = 0;
+                    while (!ok)
+                        asm volatile("{\n\t.reg .pred p;\n\t"
+                                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(lbar), "r"(parity) : "memory");
+                }
+                mix(n0 - S, par ^ 1, ib == 0 ? 2 : ib - 1, a, kRevSub);
+            }
             const float *cp[8];  // delayed comb outputs of this super-step: contiguous runs
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -801,17 +828,27 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kRevSub) : "memory");  // all-pass group only
             }
-            // the all-pass group has slack against the comb chains: it also mixes and writes the PREVIOUS super-step
-            if (n0 > 0) mix(n0 - S, par ^ 1, ib == 0 ? 2 : ib - 1, a, kRevSub);
+            if (PAIR)  // my wet samples of this super-step are in the peer's buffer: release them (one arrive per thread)
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_bar + 8u * (uint32_t)(step & 1)) : "memory");
         }
         park(pre_l, pre_r, ib == 2 ? 0 : ib + 1);
-        if (PAIR) cluster_barrier(); else __syncthreads();
+        __syncthreads();
+    }
+    if (PAIR) {  // last super-step: wait for the peer's samples; nobody leaves while the peer may still store into it
+        const uint32_t lbar = (uint32_t)__cvta_generic_to_shared(xbar) + 8u * (uint32_t)((step - 1) & 1);
+        const uint32_t parity = (uint32_t)(((step - 1) >> 1) & 1);
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(lbar), "r"(parity) : "memory");
     }
     {   // the last super-step is mixed by everybody
         const int64_t nsteps = (L + S - 1) / S;
         const int64_t m0 = (nsteps - 1) * S;
         mix(m0, (int)((nsteps - 1) & 1), (int)((nsteps - 1) % 3), tid, kRevThreads);
     }
+    if (PAIR) cluster_barrier();  // keep my shared memory alive until the peer has finished with it
     if (out_peak != nullptr) {
         pk = warp_max(pk);
         if (lane == 0) atomic_peak(out_peak, p, pk);
@@ -966,7 +1003,7 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
             for (int j = 0; j < 8; ++j) fg.comb_delay[c][j] = g.comb_size[c][j];
             for (int j = 0; j < 4; ++j) fg.ap_delay[c][j] = g.ap_size[c][j];
         }
-        const size_t smem = (size_t)(8 * kCombRing + 4 * kApRing + 10 * kRevMaxS) * sizeof(float);
+        const size_t smem = (size_t)(8 * kCombRing + 4 * kApRing + 10 * kRevMaxS) * sizeof(float) + 16;
         using Kern = void (*)(SigView, const float *, float *, int, int64_t, ReverbFastGeom, const ReverbParams *, unsigned *);
         const bool pair = stereo != 0;
         Kern kern = pair ? (seg == kRevMaxSegF ? reverb_core_kernel<kRevMaxSegF, true> : reverb_core_kernel<32, true>)
