@@ -908,11 +908,10 @@ cudaError_t launch_eq(cudaStream_t st, SigView in, const float *in_peak, float *
     eq_chunk_kernel<false><<<grid, 128, 0, st>>>(in, in_peak, nullptr, chs, L, K, coefs, scratch_f, nullptr);
     {
         constexpr int smem = kEqStates * kStitchTile * (int)sizeof(double);
-        static bool configured = false;
-        if (!configured) {
+        // per-device attribute (a process may drive several GPUs): set on every launch, it is cheap
+        {
             cudaError_t e = cudaFuncSetAttribute(eq_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
-            configured = true;
         }
         eq_stitch_kernel<<<streams, kStitchThreads, smem, st>>>(chs, K, coefs, scratch_f, scratch_s);
     }
@@ -924,11 +923,10 @@ cudaError_t launch_eq(cudaStream_t st, SigView in, const float *in_peak, float *
 cudaError_t launch_compressor(cudaStream_t st, SigView in, const float *in_peak, float *out, int P,
                               int chs, int64_t L, const CompParams *prm, unsigned *out_peak,
                               int *launches) {
-    static bool configured = false;
-    if (!configured) {
+    // per-device attribute (a process may drive several GPUs): set on every launch, it is cheap
+    {
         cudaError_t e = cudaFuncSetAttribute(compressor_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCsSmem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     compressor_scan_kernel<<<P * chs, kCsT, kCsSmem, st>>>(in, in_peak, out, chs, L, prm, out_peak);
     *launches += 1;

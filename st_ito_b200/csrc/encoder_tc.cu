@@ -852,11 +852,10 @@ template <int BN, int STAGES, int SLABK, int MT = 1>
 int launch_conv_tc_t(cudaStream_t st, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh,
                      const CUtensorMap &bl, const ConvTcParams &p) {
     constexpr int smem = STAGES * (MT * 2 * kTileM * SLABK * 2 + 2 * BN * SLABK * 2) + 1024 + 256 + 2048 * 4;  // ring, align, barriers, bias
-    static bool configured = false;
-    if (!configured) {
+    // per-device attribute (a process may drive several GPUs): set on every launch, it is cheap
+    {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES, SLABK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return tc_fail("cudaFuncSetAttribute", cudaGetErrorString(e));
-        configured = true;
     }
     const int total = ((p.mtiles + MT - 1) / MT) * p.ntiles * (p.gemm ? 16 : 1);
     const int grid = total < num_sms() ? total : num_sms();  // persistent: one CTA per SM
@@ -1054,11 +1053,10 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, con
         if (make_act_map(&al, in_lo, N, H, W, 64, 16, kC64BoxRows, 1)) return -1;
         if (make_w_map(&bh_, l.w_hi, 64, 9 * 64, 64)) return -1;
         if (make_w_map(&bl, l.w_lo, 64, 9 * 64, 64)) return -1;
-        static bool configured = false;
-        if (!configured) {
+        // per-device attribute (a process may drive several GPUs): set on every launch, it is cheap
+        {
             cudaError_t e = cudaFuncSetAttribute(conv3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC64Smem);
             if (e != cudaSuccess) return tc_fail("cudaFuncSetAttribute", cudaGetErrorString(e));
-            configured = true;
         }
         const int grid = p.mtiles < num_sms() ? p.mtiles : num_sms();
         conv3x3_c64_kernel<<<grid, kConvThreads, kC64Smem, st>>>(ah, al, bh_, bl, p);
