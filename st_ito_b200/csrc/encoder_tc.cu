@@ -165,6 +165,9 @@ struct ConvTcParams {
     // GEMM mode (Winograd): 16 independent products M_x[Tp, Cout] = V_x[Tp, Cin] * U_x[Cout, Cin]^T; A / B are 2-D maps
     // over [16 * Tp][Cin] and [16 * Cout][Cin]; the raw fp32 accumulators go to out_f32[(x * Tp + row) * Cout + col]
     int gemm, gemm_Tp;
+    // Compensation of the tensor core's truncating fp32 accumulate: every drained chunk partial sum is multiplied by
+    // 1 + trunc_comp * (number of K = 16 MMA steps accumulated into it); see chunk_comp().
+    float trunc_comp;
 };
 
 constexpr int kTileM = 128;
@@ -398,13 +401,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                 mbar_wait(&acc_full[a], (c / kAccStages) & 1);
                 tc_fence_after();
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccCols + half * kCols;
+                const int slabs_here = min(p.chunk_slabs, nslabs - ch * p.chunk_slabs);
+                const float comp = 1.0f + p.trunc_comp * (float)(slabs_here * (SLABK / 16) * 3);
 #pragma unroll
                 for (int j0 = 0; j0 < kCols; j0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(t0 + j0, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j0 + j] = __fadd_rn(acc[j0 + j], __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j) acc[j0 + j] = fmaf(__uint_as_float(v[j]), comp, acc[j0 + j]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -554,9 +559,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_c64_kernel(const __gr
                 tmem_ld32(t0, v);
                 tmem_ld32(t0 + BN, u);
                 tmem_ld_wait();
+                const float comp = 1.0f + p.trunc_comp * 12.0f;  // the main columns saw 12 accumulation steps
 #pragma unroll
                 for (int j = 0; j < kCols; ++j)
-                    acc[j] = __fadd_rn(acc[j], __fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j])));
+                    acc[j] = __fadd_rn(acc[j], fmaf(__uint_as_float(v[j]), comp, __uint_as_float(u[j])));
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
@@ -916,6 +922,21 @@ bool use_c64() {  // STITO_TC_C64=0 falls back to the generic kernel for block 1
     return v != 0;
 }
 
+// The tensor core's fp32 accumulate rounds toward zero: every K = 16 MMA step shrinks the running sum by a tiny,
+// systematic relative amount.  Measured on B200 by scanning this factor against the fp32 oracle (centred-head golden
+// fixture, K = 256 chunks): embedding error 5.9e-5 at 0, 1.2e-5 at 0.25, 6.5e-5 at 0.5, 1.9e-4 at 1.0 (units of 2^-24
+// per step) -- a clean V with its minimum at ~0.24, where the error reaches the level of the fp32 CUDA-core mode
+// (9e-6).  Every drained chunk is therefore multiplied by 1 + 0.25 * 2^-24 * steps.  STITO_TC_COMP overrides.
+float chunk_comp() {
+    static float v = -1.0f;
+    if (v < 0.0f) {
+        float a = 0.25f;
+        if (const char *e = getenv("STITO_TC_COMP")) a = (float)atof(e);
+        v = a * 5.9604644775390625e-08f;
+    }
+    return v;
+}
+
 inline int blocks_for(int64_t total, int threads) {
     int64_t b = (total + threads - 1) / threads;
     const int64_t cap = 148 * 32;
@@ -1025,6 +1046,7 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, con
     p.bias = l.bias; p.unscale = l.w_unscale / kActScale;
     p.out_scale = out_f32 ? 1.0f : (pool ? 0.25f * kActScale : kActScale);  // exact powers of two
     p.pool = pool ? 1 : 0;
+    p.trunc_comp = chunk_comp();
     p.out_hi = out_hi; p.out_lo = out_lo; p.out_f32 = out_f32;
     p.N = N; p.H = H; p.W = W; p.Cin = l.cin; p.Cout = l.cout;
     p.BW = W < 64 ? W : 64;
@@ -1107,6 +1129,7 @@ static int conv_wino(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, const
     p.mtiles = Tp / kTileM;
     p.ntiles = l.cout / 256;
     p.gemm = 1; p.gemm_Tp = Tp;
+    p.trunc_comp = chunk_comp();
     p.out_f32 = M;
     p.unscale = 1.0f; p.out_scale = 1.0f;
     const int slabk = slab_k(l.cin);
