@@ -295,7 +295,7 @@ def run_ours(args, rank, world, local_rank):
     executed_tflops = executed / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     peak = peaks["tflops_sustained"]
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01d_conv_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01e_conv_traffic.json")
     if tc and P == 64 and abs(args.seconds - 10.0) < 1e-9 and os.path.isfile(tpath):
         with open(tpath) as f:
             tj = json.load(f)
