@@ -977,7 +977,7 @@ void reverb_geometry(double sample_rate, ReverbGeom *g) {
 
 cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
                           int stereo, int64_t L, const ReverbGeom &g, const ReverbParams *prm,
-                          unsigned *out_peak, float *wet_scratch, int *launches) {
+                          unsigned *out_peak, int *launches) {
     if (g.block < 32) return cudaErrorInvalidValue;  // sample rate too low for the block scheme
     cudaError_t e;
     // fast path: one CTA per (candidate, channel), L / R CTAs paired in a cluster (reverb_core_kernel)
@@ -993,7 +993,6 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
     for (int c = 0; c < 2; ++c)
         for (int j = 0; j < 8; ++j) min_comb = g.comb_size[c][j] < min_comb ? g.comb_size[c][j] : min_comb;
     const int seg = min_comb >= 32 * kRevMaxSegF ? kRevMaxSegF : 32;
-    (void)wet_scratch;
     if (min_comb >= 32 * seg && max_comb <= 2 * 32 * seg &&
         max_ap + kRevSub <= kApRing && min_ap >= kRevSub) {
         ReverbFastGeom fg;

@@ -171,7 +171,7 @@ struct stito_handle {
     int n_fft = 2048, hop = 1024, n_mels = 128, embed_dim = 512;
 
     // work buffers
-    DevBuf audio[2], wet, eq_f, eq_s, params, peaks, Wdev, feat, act[3], pooled, emb, fit, flags, xin;
+    DevBuf audio[2], eq_f, eq_s, params, peaks, Wdev, feat, act[3], pooled, emb, fit, flags, xin;
     HostBuf hparams, hW;
     ReverbGeom rgeom{};
     TcWorkspace tcws;
@@ -363,7 +363,7 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
             case STITO_FX_REVERB: {
                 const int stereo = (cur_chs == 2 && d.num_channels == 2) ? 1 : 0;
                 cudaError_t e = launch_reverb(st, cur, in_peak, out, P, cur_chs, stereo, L, h->rgeom,
-                                              reinterpret_cast<const ReverbParams *>(slot), opk, nullptr, launches);
+                                              reinterpret_cast<const ReverbParams *>(slot), opk, launches);
                 if (e == cudaErrorInvalidValue) return fail(STITO_EINVAL, "reverb: unsupported sample rate %.1f", c.sample_rate);
                 CU(e);
                 break;
@@ -559,7 +559,7 @@ void stito_destroy(stito_handle *h) {
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     cudaDeviceSynchronize();
     for (void *p : h->owned) cudaFree(p);
-    DevBuf *bufs[] = {&h->input, &h->target, &h->audio[0], &h->audio[1], &h->wet, &h->eq_f, &h->eq_s, &h->params,
+    DevBuf *bufs[] = {&h->input, &h->target, &h->audio[0], &h->audio[1], &h->eq_f, &h->eq_s, &h->params,
                       &h->peaks, &h->Wdev, &h->feat, &h->act[0], &h->act[1], &h->act[2], &h->pooled,
                       &h->emb, &h->fit, &h->flags, &h->xin};
     for (DevBuf *b : bufs) b->release();

@@ -48,10 +48,10 @@ cudaError_t launch_delay(cudaStream_t st, SigView in, const float *in_peak, floa
                          int64_t L, const DelayParams *prm, int max_d, unsigned *out_peak,
                          int *launches);
 // stereo != 0: one joint stereo Freeverb per candidate (chs must be 2); else one mono Freeverb
-// per (candidate, channel).  wet_scratch is unused (kept for ABI stability of the internal launcher).
+// per (candidate, channel).
 cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
                           int stereo, int64_t L, const ReverbGeom &g, const ReverbParams *prm,
-                          unsigned *out_peak, float *wet_scratch, int *launches);
+                          unsigned *out_peak, int *launches);
 cudaError_t launch_copy(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
                         int64_t L, unsigned *out_peak, int *launches);
 // peak[i] = max |x[i, :, :]| as float bits (buffer must be zeroed first).
