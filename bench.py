@@ -138,6 +138,9 @@ def cpu_setup(x, chain_kinds):
 
     from oracle import cnn14, dsp
 
+    # the CPU arm uses every host thread it can: torchrun exports OMP_NUM_THREADS=1, which would cripple the baseline
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
     dsp.build()
     plugins, D, _ = dsp.load_plugins(dsp.make_plugins(chain_kinds))
     model = cnn14.make_encoder(seed=3)
