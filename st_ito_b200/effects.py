@@ -7,7 +7,7 @@ The classes carry only parameters; ``process`` renders on the B200 through libst
 ``run_es`` the whole chain is compiled into one descriptor and rendered for the entire population
 at once (st_ito_b200/engine.py) -- ``process`` is the single-plugin entry the protocol requires.
 
-Arithmetic notes (what the kernels implement; CPU restatement in oracle/dsp_oracle.c):
+Arithmetic notes (what the kernels implement; the CPU restatement used by the tests lives in the oracle package):
   * BasicParametricEQ   RBJ low-shelf + 4 peaking + high-shelf, DF-II-transposed, fp64
                         (reference effects.py:395-512 + scipy.signal.lfilter)
   * BasicCompressor     pedalboard.Compressor = juce::dsp::Compressor<float>      [recollection]
