@@ -65,6 +65,7 @@ def _signals(L=600):
 
 def _run(module, cma_mod, seed, **kw):
     """run_es of `module` with numpy's global RNG and the CMA-ES seeded identically."""
+    kw = dict(kw)
     class SeededES(cma_mod.CMAEvolutionStrategy):
         def __init__(self, x0, sigma0, opts=None):
             o = dict(opts or {})
@@ -79,7 +80,7 @@ def _run(module, cma_mod, seed, **kw):
     ToyTilt.seen_lengths = []
     with contextlib.redirect_stdout(io.StringIO()):
         plugins, D, _ = module.load_plugins(_plugins(ToyTilt))
-        x, t = _signals()
+        x, t = _signals(kw.pop("L", 600))
         res = module.run_es(x, t, SR, plugins, None, toy_embed, **kw)
     return res, x, t, list(ToyTilt.seen_lengths), D
 
@@ -105,7 +106,9 @@ def test_generic_run_es_invariants():
 
 @pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
 @pytest.mark.parametrize("kw", [dict(max_iters=6, popsize=6, sigma0=0.33, find_w0=True),
-                                dict(max_iters=16, popsize=4, sigma0=0.05, find_w0=False)])
+                                dict(max_iters=16, popsize=4, sigma0=0.05, find_w0=False),
+                                dict(max_iters=3, popsize=4, sigma0=0.2, find_w0=True, random_crop=True, L=300000),
+                                dict(max_iters=2, popsize=4, sigma0=0.2, find_w0=False, parallel=False, L=270000)])
 def test_generic_run_es_matches_the_reference_loop(kw):
     """Same plugins, same embedding function, same CMA-ES class and seeds through the reference's run_es and ours."""
     from st_ito_b200 import cma, style_transfer
