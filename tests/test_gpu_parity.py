@@ -521,3 +521,28 @@ def test_eval_population_view_equals_cropped_input(models_centred):
     eng.set_input(np.ascontiguousarray(x[:, start:start + length]))
     f_crop, _, _ = eng.eval_population(W, 0, length)
     np.testing.assert_allclose(f_view.numpy(), f_crop.numpy(), rtol=0, atol=1e-6)
+
+
+def test_fused_run_es_equals_the_candidate_by_candidate_loop(models_centred):
+    """The fused path (one stito_eval_population per generation) against the reference-shaped generic loop of the
+    same run_es (process_audio per candidate, then embed_func on the stacked audio): CMA-ES only consumes the ranking,
+    so identical rankings give a bit-identical search trajectory."""
+    from st_ito_b200.style_transfer import run_es
+    from st_ito_b200.utils import get_param_embeds
+
+    ours, _ = models_centred
+    ours.stito_engine().set_precision(1)
+    x = test_signal(2, 60000, seed=21)
+    tgt = test_signal(2, 60000, seed=22)
+
+    def run(embed):
+        plugins, D, _ = native_plugins(["eq", "comp", "reverb"])
+        return run_es(torch.from_numpy(x[None].copy()), torch.from_numpy(tgt[None].copy()), SR, plugins, ours, embed,
+                      max_iters=3, popsize=8, sigma0=0.33, find_w0=True, seed=5, verbose=False)
+
+    fused = run(get_param_embeds)
+    generic = run(lambda a, m, sr: get_param_embeds(a, m, sr))  # not `is get_param_embeds` -> generic loop
+    np.testing.assert_array_equal(fused["wopt"], generic["wopt"])
+    np.testing.assert_allclose(fused["fval_history"][1:], generic["fval_history"][1:], rtol=0, atol=2e-5)
+    assert abs(fused["fopt"] - generic["fopt"]) < 2e-5
+    np.testing.assert_array_equal(fused["output_audio"].numpy(), generic["output_audio"].numpy())
