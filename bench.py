@@ -216,8 +216,12 @@ def run_ours(args, rank, world, local_rank):
     eng.set_input(x)
     x_pinned = torch.from_numpy(x).pin_memory()
 
-    def population(step):  # seeded, sampler-independent populations; distinct per rank
-        return np.random.RandomState(1000 * (rank + 1) + step).rand(P, D)
+    # seeded, sampler-independent populations, distinct per rank and per step; drawn before the timed
+    # region (they are the synthetic inputs of the steps; uploading them IS timed)
+    _pops = {s: np.random.RandomState(1000 * (rank + 1) + s).rand(P, D) for s in range(args.warmup + args.steps)}
+
+    def population(step):
+        return _pops[step]
 
     def barrier():
         if world > 1:
