@@ -589,36 +589,41 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_c64_kernel(const __gr
 constexpr int kWinoMinCin = 1024;
 constexpr float kWinoVScale = 0.25f;  // V is stored as B^T (64 d) B / 4 = 16 (B^T d B): head-room for the 4-term sums
 
-// in (hi, lo) NHWC [N][H][W][C] (values * 64) -> V (hi, lo) [16][Tp][C] (values * 16); thread = (tile, channel pair)
+// in (hi, lo) NHWC [N][H][W][C] (values * 64) -> V (hi, lo) [16][Tp][C] (values * 16); thread = (tile, 4 channels):
+// 8-byte loads / stores, a warp covers 256 contiguous bytes of every pixel / transformed component
 __global__ void __launch_bounds__(256) wino_in_kernel(const __half *__restrict__ in_hi, const __half *__restrict__ in_lo,
                                                       __half *__restrict__ v_hi, __half *__restrict__ v_lo, int N, int H,
                                                       int W, int C, int th, int tw, int Tp) {
-    const int C2 = C >> 1;
-    const int64_t total = (int64_t)N * th * tw * C2;
+    const int C4 = C >> 2;
+    const int64_t total = (int64_t)N * th * tw * C4;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c2 = (int)(idx % C2);
-        const int tile = (int)(idx / C2);
+        const int c4 = (int)(idx % C4);
+        const int tile = (int)(idx / C4);
         const int tx = tile % tw, ty = (tile / tw) % th, n = tile / (tw * th);
-        float d0[4][4], d1[4][4];  // the two channels of the pair
+        uint2 rh[16], rl[16];  // raw hi / lo of the 4 x 4 patch (4 channels each): all loads in flight before any use
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int hh = 2 * ty - 1 + i, ww = 2 * tx - 1 + j;
-                float a = 0.f, b = 0.f;
+                uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
                 if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-                    const size_t o = (((size_t)n * H + hh) * W + ww) * C + 2 * c2;
-                    const __half2 h = *reinterpret_cast<const __half2 *>(in_hi + o);
-                    const __half2 l = *reinterpret_cast<const __half2 *>(in_lo + o);
-                    a = __low2float(h) + __low2float(l);
-                    b = __high2float(h) + __high2float(l);
+                    const size_t o = (((size_t)n * H + hh) * W + ww) * C + 4 * c4;
+                    a = __ldg(reinterpret_cast<const uint2 *>(in_hi + o));
+                    b = __ldg(reinterpret_cast<const uint2 *>(in_lo + o));
                 }
-                d0[i][j] = a; d1[i][j] = b;
+                rh[i * 4 + j] = a; rl[i * 4 + j] = b;
             }
+        uint2 oh[16], ol[16];
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            float (&d)[4][4] = ch ? d1 : d0;
-            float t[4][4];
+        for (int ch = 0; ch < 4; ++ch) {
+            float d[4][4], t[4][4];
+#pragma unroll
+            for (int x = 0; x < 16; ++x) {
+                const uint32_t wh = (ch < 2) ? rh[x].x : rh[x].y, wl = (ch < 2) ? rl[x].x : rl[x].y;
+                const __half2 h = *reinterpret_cast<const __half2 *>(&wh), l = *reinterpret_cast<const __half2 *>(&wl);
+                d[x >> 2][x & 3] = (ch & 1) ? (__high2float(h) + __high2float(l)) : (__low2float(h) + __low2float(l));
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {  // B^T d
                 t[0][j] = d[0][j] - d[2][j];
@@ -633,15 +638,24 @@ __global__ void __launch_bounds__(256) wino_in_kernel(const __half *__restrict__
                 d[i][2] = (t[i][2] - t[i][1]) * kWinoVScale;
                 d[i][3] = (t[i][1] - t[i][3]) * kWinoVScale;
             }
+#pragma unroll
+            for (int x = 0; x < 16; ++x) {
+                const float v = d[x >> 2][x & 3];
+                const __half hv = __float2half_rn(v);
+                const __half lv = __float2half_rn(v - __half2float(hv));
+                const uint32_t hb = (uint32_t)__half_as_ushort(hv) << ((ch & 1) * 16);
+                const uint32_t lb = (uint32_t)__half_as_ushort(lv) << ((ch & 1) * 16);
+                if (ch == 0) { oh[x].x = hb; ol[x].x = lb; }
+                else if (ch == 1) { oh[x].x |= hb; ol[x].x |= lb; }
+                else if (ch == 2) { oh[x].y = hb; ol[x].y = lb; }
+                else { oh[x].y |= hb; ol[x].y |= lb; }
+            }
         }
 #pragma unroll
         for (int x = 0; x < 16; ++x) {
-            const float a = d0[x >> 2][x & 3], b = d1[x >> 2][x & 3];
-            const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-            const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
-            const size_t o = ((size_t)x * Tp + tile) * C + 2 * c2;
-            *reinterpret_cast<__half2 *>(v_hi + o) = __halves2half2(ha, hb);
-            *reinterpret_cast<__half2 *>(v_lo + o) = __halves2half2(la, lb);
+            const size_t o = ((size_t)x * Tp + tile) * C + 4 * c4;
+            *reinterpret_cast<uint2 *>(v_hi + o) = oh[x];
+            *reinterpret_cast<uint2 *>(v_lo + o) = ol[x];
         }
     }
 }
@@ -1122,7 +1136,7 @@ static int conv_wino(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, const
     if (ws_ensure(ws, 6, (size_t)16 * Tp * l.cout * sizeof(float))) return -1;
     __half *v_hi = (__half *)ws.buf[4], *v_lo = (__half *)ws.buf[5];
     float *M = (float *)ws.buf[6];
-    wino_in_kernel<<<blocks_for((int64_t)T * (l.cin / 2), 256), 256, 0, st>>>(in_hi, in_lo, v_hi, v_lo, N, H, W, l.cin, th, tw, Tp);
+    wino_in_kernel<<<blocks_for((int64_t)T * (l.cin / 4), 256), 256, 0, st>>>(in_hi, in_lo, v_hi, v_lo, N, H, W, l.cin, th, tw, Tp);
     ConvTcParams p{};
     p.N = N; p.H = H; p.W = W; p.Cin = l.cin; p.Cout = l.cout;
     p.BW = 16; p.BH = 8; p.IPT = 1; p.tilesW = 1; p.tilesH = 1;  // unused in GEMM mode
