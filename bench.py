@@ -294,11 +294,14 @@ def run_ours(args, rank, world, local_rank):
     ms_layers = [float(v) / K for v in conv_ms]
     tc_flop, tc_ms = sum(layer_flop[1:]), sum(ms_layers[1:])
     achieved = tc_flop / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
-    # tensor-pipe work actually executed: 3 MMAs per MAC (fp16x3); the Cin >= 1024 layers (10, 11, 12) run as Winograd
-    # F(2x2,3x3) GEMMs with 4/9 of the direct MACs unless STITO_TC_WINOGRAD=0
+    # tensor-pipe work actually executed: 3 MMAs per MAC (fp16x3); layers with Cin*Cout/(Cin+Cout) >= 340 (conv 9..12)
+    # run as Winograd F(2x2,3x3) GEMMs with 4/9 of the direct MACs unless STITO_TC_WINOGRAD=0
     wino = os.environ.get("STITO_TC_WINOGRAD", "1") != "0"
+    wthr = int(os.environ.get("STITO_TC_WINO_MIN", "340"))
     cin = [1, 64, 64, 128, 128, 256, 256, 512, 512, 1024, 1024, 2048]
-    executed = sum(f * 3.0 * ((4.0 / 9.0) if (wino and c >= 1024) else 1.0) for f, c in zip(layer_flop[1:], cin[1:]))
+    cout = [64, 64, 128, 128, 256, 256, 512, 512, 1024, 1024, 2048, 2048]
+    executed = sum(f * 3.0 * ((4.0 / 9.0) if (wino and ci >= 512 and ci * co >= wthr * (ci + co)) else 1.0)
+                   for f, ci, co in zip(layer_flop[1:], cin[1:], cout[1:]))
     executed_tflops = executed / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     peak = peaks["tflops_sustained"]
     traffic = None
@@ -315,7 +318,7 @@ def run_ours(args, rank, world, local_rank):
                                             "profiles/r01e_conv_traffic.json)",
         "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)",
         "note": "achieved = algorithmic (direct-convolution) 2*MAC of conv layers 2..12 (%.2f GFLOP per stereo candidate) / "
-                "CUDA-event time of those layers; the fp16x3 scheme executes 3 tensor-core MACs per MAC and the three "
+                "CUDA-event time of those layers; the fp16x3 scheme executes 3 tensor-core MACs per MAC and the four "
                 "deepest layers run as Winograd GEMMs (4/9 of the MACs): see tensor_pipe_executed_tflops" % (tc_flop / P / 1e9),
         "tensor_pipe_executed_tflops": executed_tflops if tc else None,
         "ms_per_layer": ms_layers,

@@ -579,14 +579,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_c64_kernel(const __gr
 // Y = A^T [ (G g G^T) . (B^T d B) ] A turns the 3x3 convolution of a 4x4 input tile d (stride 2) into 16 independent
 // channel contractions -- 16 GEMMs  M_x[tiles, Cout] = V_x[tiles, Cin] U_x[Cout, Cin]^T  with 4/9 of the direct
 // convolution's MACs.  The price is a 4x larger transformed activation (V) and an fp32 M round trip, so it pays only
-// where the activations are small next to the weights: Cin >= 1024 (b5c2, b6c1, b6c2).  V and U are split into fp16
+// where the activations are small next to the weights: b5c1, b5c2, b6c1, b6c2 (see wino_layer()).  V and U are split into fp16
 // hi/lo pairs like every other operand and the GEMMs run in conv3x3_tc_kernel's GEMM mode (same fp16x3 MMAs, same
 // chunked fp32 accumulation); CPU emulation of this exact scheme: 4.5e-6 relative embedding error on the
 // centred-head fixture (tests/dev/dev_emulate_winograd.py).
-// Layers with at least this many input channels use the Winograd path.  Saved MACs and transform traffic both scale with
-// the pixel count, so the break-even depends on Cin*Cout/(Cin+Cout) only; measured on B200 (P = 64): 512->512 +20 %,
-// 512->1024 +-0 %, 1024->1024 -15 %, 1024->2048 -33 %, 2048->2048 -43 %.
-constexpr int kWinoMinCin = 1024;
+constexpr int kWinoMinCin = 512;   // U is prepared from here on; the dispatch rule is wino_layer()
 constexpr float kWinoVScale = 0.25f;  // V is stored as B^T (64 d) B / 4 = 16 (B^T d B): head-room for the 4-term sums
 
 // in (hi, lo) NHWC [N][H][W][C] (values * 64) -> V (hi, lo) [16][Tp][C] (values * 16); thread = (tile, 4 channels):
@@ -924,6 +921,19 @@ bool use_mt2() {  // STITO_TC_MT2=0: one M tile per work item on the Cout = 128 
     return v != 0;
 }
 
+// Winograd pays when the weights are large next to the activations.  Saved MACs and transform traffic both scale with
+// the pixel count, so the break-even depends on Cin*Cout/(Cin+Cout) only; measured on B200 (P = 64, 10 s):
+// 512->512 (256): +8 %, 512->1024 (341): -11 %, 1024->1024 (512): -24 %, 1024->2048 (683): -37 %, 2048->2048 (1024): -47 %.
+// Threshold 340 selects the last four; STITO_TC_WINO_MIN overrides it (developer knob).
+bool wino_layer(const ConvLayer &l) {
+    static int thr = -1;
+    if (thr < 0) {
+        thr = 340;
+        if (const char *e = getenv("STITO_TC_WINO_MIN")) { const int t = atoi(e); if (t > 0) thr = t; }
+    }
+    return l.u_hi != nullptr && (int64_t)l.cin * l.cout >= (int64_t)thr * (l.cin + l.cout);
+}
+
 bool use_wino() {  // STITO_TC_WINOGRAD=0: direct implicit-GEMM convolution on every layer (developer knob)
     static int v = -1;
     if (v < 0) { const char *e = getenv("STITO_TC_WINOGRAD"); v = (e && atoi(e) == 0) ? 0 : 1; }
@@ -1185,12 +1195,12 @@ int tc_encoder_forward(cudaStream_t st, const EncoderDev &enc, TcWorkspace &ws, 
             tc_conv_first_kernel<<<blocks_for((int64_t)px * 8 / kC1Px, 256), 256, 0, st>>>(feat, l1.w, l1.bias, m_hi, m_lo, N, H, W);
             *launches += 1;
         } else {
-            if (l1.u_hi != nullptr && use_wino()) {
+            if (wino_layer(l1) && use_wino()) {
                 if (conv_wino(st, l1, ws, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
             } else if (conv_tc(st, l1, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
         }
         if (ev) cudaEventRecord(ev[2 * b + 1], st);
-        const bool wino2 = l2.u_hi != nullptr && use_wino();
+        const bool wino2 = wino_layer(l2) && use_wino();
         if (b < 5) {  // conv2 + ReLU + 2x2 average pool + hi/lo split in one kernel -> next block's input
             if (wino2) {
                 if (conv_wino(st, l2, ws, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
