@@ -305,7 +305,7 @@ def run_ours(args, rank, world, local_rank):
     executed_tflops = executed / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     peak = peaks["tflops_sustained"]
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01e_conv_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01f_conv_traffic.json")
     if tc and P == 64 and abs(args.seconds - 10.0) < 1e-9 and os.path.isfile(tpath):
         with open(tpath) as f:
             tj = json.load(f)
@@ -315,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
                    "precision), conv layers 2..12 of every generation") if tc else "conv3x3 fp32 CUDA-core kernel (precision 0)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": traffic, "traffic_unit": "bytes per launch (mean of the 11 launches; ncu dram read+write, "
-                                            "profiles/r01e_conv_traffic.json)",
+                                            "profiles/r01f_conv_traffic.json)",
         "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)",
         "note": "achieved = algorithmic (direct-convolution) 2*MAC of conv layers 2..12 (%.2f GFLOP per stereo candidate) / "
                 "CUDA-event time of those layers; the fp16x3 scheme executes 3 tensor-core MACs per MAC and the four "
