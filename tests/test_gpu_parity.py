@@ -546,3 +546,40 @@ def test_fused_run_es_equals_the_candidate_by_candidate_loop(models_centred):
     np.testing.assert_allclose(fused["fval_history"][1:], generic["fval_history"][1:], rtol=0, atol=2e-5)
     assert abs(fused["fopt"] - generic["fopt"]) < 2e-5
     np.testing.assert_array_equal(fused["output_audio"].numpy(), generic["output_audio"].numpy())
+
+
+def test_config4_shape_30s_stereo(models_centred, oracle_dsp):
+    """BASELINE config 4's shape (30 s stereo, L = 1 440 000, T = 1407): other tile geometries in every kernel (odd
+    heights 1407 / 703 / 351 / 175 / 87 / 43, 94 compressor super-blocks, 1286 reverb super-steps).  Waveform of one
+    candidate against the oracle, and the target's own parameters must score -1 and win."""
+    from st_ito_b200.engine import compile_chain
+    from st_ito_b200.style_transfer import process_audio
+
+    ours, _ = models_centred
+    eng = ours.stito_engine()
+    eng.set_precision(1)
+    kinds = ["eq", "comp", "reverb"]
+    plugins, D, _ = native_plugins(kinds)
+    oplugins, _, _ = oracle_plugins(oracle_dsp, kinds)
+    L = 1440000
+    x = test_signal(2, L, seed=31)
+    x = x / np.abs(x).max()
+    rng = np.random.RandomState(44)
+    w_star = rng.rand(D)
+    W = rng.rand(3, D)
+    W[1] = w_star
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    eng.set_input(x)
+    tgt = process_audio(x, w_star, SR, plugins)
+    eng.set_target(tgt)
+    fit, _, aud = eng.eval_population(W, 0, L, want_audio=True, in_chs=2)
+    assert abs(fit[1].item() + 1.0) < 1e-5 and int(torch.argmin(fit)) == 1
+    assert torch.isfinite(fit).all() and fit[0].item() > -1.0 + 1e-4 and fit[2].item() > -1.0 + 1e-4
+    ref0 = oracle_dsp.process_audio(x, W[0], SR, oplugins)
+    # Every stage alone matches the oracle to <= 1.2e-7 (EQ 1e-12, compressor 1e-7, Freeverb bit-exact) at this length;
+    # chained, the compressor's 1e-7 differences flip some of Freeverb's "+0.1 - 0.1" roundings (7.5e-9 steps) inside
+    # comb loops with feedback up to 0.98, which is rounding noise of ~1e-6 mean / 1.4e-5 max over 2.9 M samples.
+    err = np.abs(aud[0].numpy() - ref0)
+    assert err.max() <= 3e-5 and err.mean() <= 5e-6, (err.max(), err.mean())
+    np.testing.assert_array_equal(aud[1].numpy(), tgt)
