@@ -1,25 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- ES candidates/sec of the population-evaluation hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pop P] [--seconds S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C] [--pop P] [--weak]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one CMA-ES generation: evaluate(W) for a population of P candidates: render
-each candidate through the effect chain (EQ -> Compressor -> Reverb), log-mel, AFx-Rep encoder, cosine
-fitness against the target's mid/side embeddings.  Workload = BASELINE config 2 (10 s stereo 48 kHz,
-P = 64, "mastering-pb" chain) per GPU; with N GPUs every rank evaluates its own P candidates (weak
-scaling, the population is sharded) and the fitness values are all-gathered over NCCL each generation.
+Workload (default = BASELINE config 2): 10 s stereo 48 kHz input, "mastering-pb" chain (EQ -> Compressor -> Reverb,
+D = 29), CMA-ES with a population of 64, AFx-Rep (Cnn14) embedding metric, 25 generations per ES run.
 
-value  : candidates/s with the input waveform resident in HBM (the per-generation parameter block W,
-         P*D doubles, is the only H2D traffic inside the timed region).
-e2e    : candidates/s through the host-buffer API -- every step uploads the input waveform and W from
-         pinned host memory and reads fitness + embeddings back.
-The reference arm (--impl reference) and cpu_baseline time the CPU oracle (a restatement of the
-reference's CPU path: the reference itself is pure Python over scipy/pedalboard/torch and cannot be
-installed offline) on this box's host cores.
+A "step" is one ES run segment of `--iters` generations (25) driven by the real host loop:
+    W = es.ask()  ->  evaluate(W) [render every candidate, log-mel, encoder, cosine fitness]  ->  es.tell(W, fvals)
+with a fresh, seeded CMA-ES per step (find_w0 and the final render are outside the metric).  K steps are timed with CUDA
+events on the launch stream (max over ranks); the CMA-ES host time therefore counts (it shows up as device idle time).
+
+value  : candidates/s with the input waveform resident in HBM (per generation only the parameter block travels).
+e2e    : the same loop through the host-buffer API: EVERY generation re-uploads the input waveform from pinned host
+         memory and reads fitness + embeddings back.
+--gpus N (torchrun): STRONG scaling by default -- the population of P candidates is sharded over the N ranks
+         (P/N each) and the fitness values are all-gathered over NCCL every generation; --weak gives every rank its
+         own P candidates instead (population N*P).
+The reference arm (--impl reference) and cpu_baseline time the CPU oracle -- a restatement of the reference's CPU path;
+the reference itself is pure Python over scipy/pedalboard/torch and cannot be installed offline -- on this
+box's host cores, one generation (P candidates) per step.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -34,8 +39,43 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 SR = 48000
-METRIC = "ES candidates/sec (pop=64, 10s@48kHz stereo)"
 UNIT = "candidates/s"
+
+# BASELINE.json configs: (seconds, channels, chain preset, population, generations per ES run)
+CONFIGS = {
+    1: dict(seconds=5.0, chs=1, chain="eq", pop=8, iters=5, label="EQ-only"),
+    2: dict(seconds=10.0, chs=2, chain="mastering-pb", pop=64, iters=25, label="EQ+Compressor+Reverb (mastering-pb)"),
+    3: dict(seconds=10.0, chs=2, chain="mastering-pb", pop=256, iters=50, label="EQ+Compressor+Reverb (mastering-pb)"),
+    4: dict(seconds=30.0, chs=2, chain="mastering-conv", pop=128, iters=25,
+            label="EQ+Compressor+2s-IR convolution reverb (mastering-conv)"),
+}
+ORACLE_KINDS = {"eq": ["eq"], "mastering-pb": ["eq", "comp", "reverb"], "basic": ["eq", "comp", "dist", "delay", "reverb"],
+                "mastering-conv": ["eq", "comp", "convreverb"]}
+
+
+def resolve(args):
+    c = dict(CONFIGS[args.config])
+    if args.seconds is not None:
+        c["seconds"] = args.seconds
+    if args.pop is not None:
+        c["pop"] = args.pop
+    if args.iters is not None:
+        c["iters"] = args.iters
+    if args.chain is not None:
+        c["chain"] = args.chain
+        c["label"] = args.chain
+    return c
+
+
+def metric_name(c, pop_total):
+    return f"ES candidates/sec (pop={pop_total}, {c['seconds']:g}s@48kHz {'stereo' if c['chs'] == 2 else 'mono'})"
+
+
+def workload_label(args, c, pop_total, D):
+    """Identical in both arms (the driver compares it)."""
+    return (f"config{args.config}: {c['seconds']:g}s {'stereo' if c['chs'] == 2 else 'mono'} 48kHz, {c['label']}, "
+            f"pop={pop_total}, D={D}, {c['iters']} generations per ES run, AFx-Rep Cnn14 (seeded synthetic weights, "
+            f"centred heads)")
 
 
 def load_peaks():
@@ -49,7 +89,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -63,7 +103,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -75,7 +115,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -104,20 +144,21 @@ def make_workload(seconds, chs=2):
 
 
 # ------------------------------------------------------------------------------------- CPU arm
-def cpu_candidates(x, W, plugins, model, target_embeds):
-    """The reference's CPU path for a slice of the population: serial process_audio per candidate
-    (style_transfer.py:512-521) then one batched encoder call with all host threads."""
+def cpu_candidates(x, W, plugins, model, target_embeds, serial=False):
+    """The reference's CPU path for a population: process_audio per candidate -- on a pool of host threads like the
+    reference's `parallel=True` branch (style_transfer.py:499-502; the oracle's C kernels release the GIL), or one
+    after the other like its default branch (:512-521) with serial=True -- then the batched encoder call on all cores."""
+    import copy
+    from concurrent.futures import ThreadPoolExecutor
+
     import torch
 
     from oracle import cnn14, dsp
 
-    import copy
-    from concurrent.futures import ThreadPoolExecutor
-
-    # DSP: one candidate per host thread (the reference's `parallel=True` pool, style_transfer.py:499-502; the
-    # oracle's C kernels release the GIL).  Plugin objects are stateful, so every worker gets its own copy.
-    workers = max(1, min(len(W), os.cpu_count() or 1))
-    pool_plugins = [copy.deepcopy(plugins) for _ in range(workers)]
+    if x.shape[-1] <= 262144:  # evaluate()'s length policy (style_transfer.py:505-518): right-zero-pad to 262144
+        x = np.pad(x, ((0, 0), (0, 262144 - x.shape[-1])))
+    workers = 1 if serial else max(1, min(len(W), os.cpu_count() or 1))
+    pool_plugins = [copy.deepcopy(plugins) for _ in range(workers)]  # plugin objects are stateful
 
     def render(job):
         k, w = job
@@ -125,25 +166,36 @@ def cpu_candidates(x, W, plugins, model, target_embeds):
 
     fits = []
     for i in range(0, len(W), 8):  # encoder in batches of 8 candidates: bounded activation memory on the host
-        with ThreadPoolExecutor(max_workers=workers) as ex:
-            rendered = list(ex.map(render, [(k, w) for k, w in enumerate(W[i:i + 8])]))
+        jobs = [(k, w) for k, w in enumerate(W[i:i + 8])]
+        if serial:
+            rendered = [render(j) for j in jobs]
+        else:
+            with ThreadPoolExecutor(max_workers=workers) as ex:
+                rendered = list(ex.map(render, jobs))
         audios = torch.stack([torch.from_numpy(a) for a in rendered])
         emb = cnn14.get_param_embeds(audios, model, SR)
         fits.append(cnn14.fitness(emb, target_embeds))
     return torch.cat(fits)
 
 
-def cpu_setup(x, chain_kinds):
+def cpu_setup(x, chain, head_bias=None):
+    """Oracle plugins / encoder for the CPU legs.  `head_bias` = (fc_mid.bias, fc_side.bias) of the GPU arm's model, so
+    that both score with the same weights; without it the heads are centred by the oracle itself."""
     import torch
 
     from oracle import cnn14, dsp
 
     # the CPU arm uses every host thread it can: torchrun exports OMP_NUM_THREADS=1, which would cripple the baseline
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-
     dsp.build()
-    plugins, D, _ = dsp.load_plugins(dsp.make_plugins(chain_kinds))
-    model = cnn14.make_encoder(seed=3)
+    plugins, D, _ = dsp.load_plugins(dsp.make_plugins(ORACLE_KINDS[chain]))
+    model = cnn14.make_encoder(seed=3, conv_gain=2.0)
+    if head_bias is None:
+        cnn14.centre_heads(model)
+    else:
+        with torch.no_grad():
+            model.fc_mid.bias.copy_(head_bias[0])
+            model.fc_side.bias.copy_(head_bias[1])
     w_star = np.random.RandomState(1234).rand(D)
     tgt = dsp.process_audio(x, w_star, SR, plugins)
     te = cnn14.get_param_embeds(torch.from_numpy(tgt[None].copy()), model, SR)
@@ -151,34 +203,41 @@ def cpu_setup(x, chain_kinds):
 
 
 def run_reference(args, rank):
-    """--impl reference: the CPU path on this box's host cores; rank 0 only."""
+    """--impl reference: the CPU path on this box's host cores; rank 0 only.  One generation (P candidates) per step."""
     if rank != 0:
         return
     import torch
 
-    x = make_workload(args.seconds)
-    plugins, D, model, te = cpu_setup(x, ["eq", "comp", "reverb"])
-    sample = args.ref_sample
+    c = resolve(args)
+    P = c["pop"]
+    x = make_workload(c["seconds"], c["chs"])
+    plugins, D, model, te = cpu_setup(x, c["chain"])
     times = []
     for step in range(args.warmup + args.steps):
-        W = np.random.RandomState(100 + step).rand(sample, D)
+        W = np.random.RandomState(100 + step).rand(P, D)
         t0 = time.perf_counter()
         cpu_candidates(x, W, plugins, model, te)
         dt = time.perf_counter() - t0
         if step >= args.warmup:
             times.append(dt)
     total = sum(times)
-    value = sample * len(times) / total
+    value = P * len(times) / total
     cores = torch.get_num_threads()
+    ns = min(P, 16)  # the reference's default branch renders the candidates one after the other
+    t0 = time.perf_counter()
+    cpu_candidates(x, np.random.RandomState(99).rand(ns, D), plugins, model, te, serial=True)
+    value_serial = ns / (time.perf_counter() - t0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(c, P), "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"config2: {args.seconds:g}s stereo 48kHz, EQ+Compressor+Reverb, pop={args.pop}",
-                   "sample": f"{sample} candidates of the population per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} candidates/step x {len(times)} steps, oracle DSP (C, serial per "
-                                   f"candidate) + torch CPU Cnn14 ({cores} threads)"},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (encoder), f64 (EQ)",
+        "data": "synthetic",
+        "config": {"workload": workload_label(args, c, P, D),
+                   "sample": f"one generation ({P} candidates) of the {c['iters']}-generation ES run per step"},
+        "cpu_baseline": {"value": value, "value_serial": value_serial, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{P} candidates/step x {len(times)} steps: oracle DSP (C, one candidate per host "
+                                   f"thread) + torch CPU Cnn14 ({cores} threads); value_serial: {ns} candidates rendered "
+                                   f"one after the other (the reference's default branch, style_transfer.py:512-521)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -187,75 +246,83 @@ def run_reference(args, rank):
 
 # ------------------------------------------------------------------------------------- GPU arm
 def run_ours(args, rank, world, local_rank):
+    import contextlib
+    import io
+
     import torch
     import torch.distributed as dist
 
-    from st_ito_b200 import effects
-    from st_ito_b200.engine import compile_chain
-    from st_ito_b200.style_transfer import load_plugins, process_audio
-    from st_ito_b200.utils import make_synthetic_param_model
+    from st_ito_b200 import cma, effects
+    from st_ito_b200.style_transfer import FusedEvaluator, load_plugins, process_audio
+    from st_ito_b200.utils import centre_heads, get_param_embeds, make_synthetic_param_model
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     peaks = load_peaks()
-    P, L = args.pop, int(args.seconds * SR)
-    x = make_workload(args.seconds)
+    c = resolve(args)
+    P_total = c["pop"] * (world if args.weak else 1)
+    L, iters = int(c["seconds"] * SR), c["iters"]
+    x = make_workload(c["seconds"], c["chs"])
 
-    import contextlib
-    import io
     with contextlib.redirect_stdout(io.StringIO()):
-        plugins, D, _ = load_plugins(effects.make_chain("mastering-pb"))
-    model = make_synthetic_param_model(seed=3)
+        plugins, D, _ = load_plugins(effects.make_chain(c["chain"]))
+    model = centre_heads(make_synthetic_param_model(seed=3, conv_gain=2.0))
     eng = model.stito_engine(local_rank)
     if args.precision is not None:
         eng.set_precision(args.precision)
-    desc, _ = compile_chain(plugins, SR)
-    eng.set_chain(desc)
     w_star = np.random.RandomState(1234).rand(D)
-    eng.set_target(process_audio(x, w_star, SR, plugins))
-    eng.set_input(x)
-    x_pinned = torch.from_numpy(x).pin_memory()
-
-    # seeded, sampler-independent populations, distinct per rank and per step; drawn before the timed
-    # region (they are the synthetic inputs of the steps; uploading them IS timed)
-    _pops = {s: np.random.RandomState(1000 * (rank + 1) + s).rand(P, D) for s in range(args.warmup + args.steps)}
-
-    def population(step):
-        return _pops[step]
+    tgt = process_audio(x, w_star, SR, plugins)
+    te = get_param_embeds(torch.from_numpy(tgt[None].copy()), model, SR)
+    x_t = torch.from_numpy(x)
+    x_pinned = x_t.pin_memory()
+    ev = FusedEvaluator(eng, plugins, SR, te, x_t[None])
+    start, length = ev.view_for(L, False)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    fit_all = torch.empty(world * P, dtype=torch.float32, device=dev) if world > 1 else None
+    record = {}  # (step, generation) -> (W, fitness): the populations the CPU leg re-scores for the parity object
 
-    def generation(step, e2e):
-        W = population(step)
-        if e2e:
-            eng.set_input(x_pinned)
-        fit, emb, _ = eng.eval_population(W, 0, L, want_embeds=e2e)
-        if world > 1:  # one all-gather of the scalar fitness values per generation
-            dist.all_gather_into_tensor(fit_all, fit.to(dev, non_blocking=True))
-        return fit
+    def es_step(step, e2e, acc=None, keep=0):
+        """One ES run segment: `iters` generations of ask -> evaluate -> tell with a fresh seeded CMA-ES."""
+        es = cma.CMAEvolutionStrategy(np.full(D, 0.5), 0.33, {"bounds": [0, 1], "popsize": P_total, "seed": 1 + step,
+                                                              "verbose": -9})
+        for g in range(iters):
+            t0 = time.perf_counter()
+            W = np.asarray(es.ask())
+            t1 = time.perf_counter()
+            if e2e:
+                eng.set_input(x_pinned, min_len=ev.crop_len)
+            fvals, emb, _ = ev(W, want_embeds=e2e)
+            t2 = time.perf_counter()
+            es.tell(list(W), fvals)
+            t3 = time.perf_counter()
+            if acc is not None:
+                t = eng.timing()
+                acc["launches"] += t["launches"]
+                for k in ("ms_dsp", "ms_frontend", "ms_encoder", "ms_fitness"):
+                    acc[k] += t[k]
+                acc["conv"] += np.array(t["ms_conv"])
+                acc["host_cma_ms"] += 1e3 * ((t1 - t0) + (t3 - t2))
+                acc["comp_fallbacks"] += t["comp_fallbacks"]
+                acc["act_overflow"] += t["act_overflow"]
+                acc["last"] = t
+            if g < keep:
+                record[(step, g)] = (W.copy(), np.array(fvals, dtype=np.float32))
 
     def timed(e2e):
         for s in range(args.warmup):
-            generation(s, e2e)
-        launches, stage = 0, {"ms_dsp": 0.0, "ms_frontend": 0.0, "ms_encoder": 0.0, "ms_fitness": 0.0}
-        conv_ms = np.zeros(12)
+            es_step(s, e2e)
+        acc = {"launches": 0, "ms_dsp": 0.0, "ms_frontend": 0.0, "ms_encoder": 0.0, "ms_fitness": 0.0,
+               "conv": np.zeros(12), "host_cma_ms": 0.0, "comp_fallbacks": 0, "act_overflow": 0, "last": None}
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record()
         for s in range(args.steps):
-            generation(args.warmup + s, e2e)
-            t = eng.timing()
-            launches += t["launches"]
-            for k in stage:
-                stage[k] += t[k]
-            conv_ms += np.array(t["ms_conv"])
-            last = t
+            es_step(args.warmup + s, e2e, acc, keep=(args.cpu_sample if (s == 0 and not e2e) else 0))
         ev1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -264,34 +331,50 @@ def run_ours(args, rank, world, local_rank):
             tt = torch.tensor([ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
-        return ms, wall, launches, stage, conv_ms, last
+            ll = torch.tensor([float(acc["launches"])], device=dev)
+            dist.all_reduce(ll, op=dist.ReduceOp.SUM)
+            acc["launches"] = int(ll.item())
+        return ms, wall, acc
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     stream = torch.cuda.Stream(dev)  # libstito launches on torch's current stream; events are recorded on it
     with torch.cuda.stream(stream):
         if sampler:
             sampler.start()
-        ms, wall, launches, stage, conv_ms, last = timed(e2e=False)
+        ms, wall, acc = timed(e2e=False)
         clocks = sampler.stop() if sampler else None
-        ms_e2e, _, _, _, _, _ = timed(e2e=True)
+        ms_e2e, _, _ = timed(e2e=True)
+        shard_check = None
+        if world > 1:
+            # sharded evaluation + all-gather must equal one rank scoring the whole population, bit for bit
+            Wc = np.random.RandomState(4242).rand(P_total, D)
+            gathered = np.array(ev(Wc)[0], dtype=np.float32)
+            whole = eng.eval_population(Wc, start, length)[0].numpy()
+            same = torch.tensor([1.0 if np.array_equal(gathered, whole) else 0.0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            shard_check = {"population": P_total, "ranks": world, "gathered_equals_single_rank_bitwise": bool(same.item() == 1.0)}
 
     if rank != 0:
         return
     K = args.steps
-    value = world * P * K / (ms / 1e3)
-    e2e_value = world * P * K / (ms_e2e / 1e3)
+    gens = K * iters
+    value = P_total * gens / (ms / 1e3)
+    e2e_value = P_total * gens / (ms_e2e / 1e3)
+    last = acc["last"]
     tc = last["precision"] == 1
-    # dominant kernel: the tcgen05 implicit-GEMM convolution (11 launches per generation: conv layers 2..12; layer 1,
-    # Cin = 1 / K = 9, is a separate memory-bound CUDA-core kernel).  Algorithmic FLOPs of those launches / their
-    # CUDA-event time on the launch stream (per-layer events recorded inside libstito).
-    T = L // 1024 + 1
+    P_rank = P_total // world if world > 1 else P_total  # candidates per rank (rank 0's shard)
+    # dominant kernel: the tcgen05 implicit-GEMM convolution (conv layers 2..12; layer 1, Cin = 1 / K = 9, is a separate
+    # memory-bound CUDA-core kernel).  Algorithmic FLOPs of those launches / their CUDA-event time on the launch stream
+    # (per-layer events recorded inside libstito), on rank 0's shard.
+    T = length // 1024 + 1
+    ochs = 2 if (c["chs"] == 2 or c["chain"] != "eq") else 1
     ch = [1, 64, 128, 256, 512, 1024, 2048]
     layer_flop, hh, ww = [], T, 128
     for b in range(6):
         layer_flop += [2.0 * hh * ww * ch[b + 1] * 9 * ch[b], 2.0 * hh * ww * ch[b + 1] * 9 * ch[b + 1]]
         hh, ww = hh // 2, ww // 2
-    layer_flop = [f * 2 * P for f in layer_flop]  # 2 signals (mid, side) per stereo candidate
-    ms_layers = [float(v) / K for v in conv_ms]
+    layer_flop = [f * ochs * P_rank for f in layer_flop]  # one log-mel image per output channel (mid, side)
+    ms_layers = [float(v) / gens for v in acc["conv"]]
     tc_flop, tc_ms = sum(layer_flop[1:]), sum(ms_layers[1:])
     achieved = tc_flop / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     # tensor-pipe work actually executed: 3 MMAs per MAC (fp16x3); layers with Cin*Cout/(Cin+Cout) >= 340 (conv 9..12)
@@ -304,73 +387,108 @@ def run_ours(args, rank, world, local_rank):
                    for f, ci, co in zip(layer_flop[1:], cin[1:], cout[1:]))
     executed_tflops = executed / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     peak = peaks["tflops_sustained"]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01f_conv_traffic.json")
-    if tc and P == 64 and abs(args.seconds - 10.0) < 1e-9 and os.path.isfile(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
+    traffic, traffic_src = None, None
+    for name in ("r02_conv_traffic.json", "r01f_conv_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if tc and world == 1 and args.config == 2 and P_total == 64 and os.path.isfile(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
             traffic = tj["dram_bytes_per_generation"] / tj["launches"]  # per launch, like `achieved`
+            traffic_src = f"profiles/{name}: ncu dram read+write of the conv-stack kernels, mean over its {tj['launches']} launches per generation"
+            break
+    stages = {k: acc[k] / gens for k in ("ms_dsp", "ms_frontend", "ms_encoder", "ms_fitness")}
     roofline = {
         "kernel": ("conv3x3_tc_kernel / conv3x3_c64_kernel (tcgen05 implicit-GEMM 3x3 conv / Winograd GEMMs, fp16x3 split "
                    "precision), conv layers 2..12 of every generation") if tc else "conv3x3 fp32 CUDA-core kernel (precision 0)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "traffic": traffic, "traffic_unit": "bytes per launch (mean of the 11 launches; ncu dram read+write, "
-                                            "profiles/r01f_conv_traffic.json)",
-        "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)",
-        "note": "achieved = algorithmic (direct-convolution) 2*MAC of conv layers 2..12 (%.2f GFLOP per stereo candidate) / "
+        "traffic": traffic, "traffic_unit": traffic_src,
+        "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS, MEASURED_PEAKS.json); the timed region is {ms / 1e3:.1f} s",
+        "note": "achieved = algorithmic (direct-convolution) 2*MAC of conv layers 2..12 (%.2f GFLOP per candidate) / "
                 "CUDA-event time of those layers; the fp16x3 scheme executes 3 tensor-core MACs per MAC and the four "
-                "deepest layers run as Winograd GEMMs (4/9 of the MACs): see tensor_pipe_executed_tflops" % (tc_flop / P / 1e9),
+                "deepest layers run as Winograd GEMMs (4/9 of the MACs): see tensor_pipe_executed_tflops" % (tc_flop / max(P_rank, 1) / 1e9),
         "tensor_pipe_executed_tflops": executed_tflops if tc else None,
         "ms_per_layer": ms_layers,
-        "stages_ms": {k: v / K for k, v in stage.items()},
-        "hbm": {"dsp_GBps": last["dsp_bytes"] / max(stage["ms_dsp"] / K, 1e-9) / 1e6,
-                "frontend_GBps": last["frontend_bytes"] / max(stage["ms_frontend"] / K, 1e-9) / 1e6,
-                "peak_GBps": peaks["hbm_gbs"]},
+        "stages_ms_per_generation": stages,
+        "hbm": {"dsp_GBps": last["dsp_bytes"] / max(stages["ms_dsp"], 1e-9) / 1e6,
+                "frontend_GBps": last["frontend_bytes"] / max(stages["ms_frontend"], 1e-9) / 1e6,
+                "peak_GBps": peaks["hbm_gbs"],
+                "note": "algorithmic bytes (SURVEY 8d) / CUDA-event time of the DSP chain and of the log-mel kernel"},
     }
+    h2d = int(x.nbytes + (P_rank if world > 1 else P_total) * D * 8)
+    d2h = int(P_rank * 4 + 2 * P_rank * 512 * 4)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": metric_name(c, P_total), "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
         "dtype": "f16x3+f32acc (encoder), f64 (EQ), f32 (comp/reverb/FFT)" if tc else "f32 (encoder), f64 (EQ)",
         "data": "synthetic",
-        "config": {"workload": f"config2: {args.seconds:g}s stereo 48kHz, EQ+Compressor+Reverb (mastering-pb), "
-                               f"pop={P} per GPU, D={D}, AFx-Rep Cnn14 seeded random weights",
-                   "l2": "per-step working set (activations > 1 GB) exceeds the 126 MB L2; no explicit flush",
-                   "parallelism": f"population sharded, {world} x {P} candidates, fitness all-gather"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes + P * D * 8),
-                "d2h_bytes_per_step": int(P * 4 + 2 * P * 512 * 4)},
-        "gpu_launches": int(launches),
+        "config": {"workload": workload_label(args, c, P_total, D),
+                   "step": f"one ES run segment = {iters} generations of ask -> evaluate -> tell (fresh seeded CMA-ES, "
+                           f"sigma0 = 0.33, bounds [0, 1]); {gens} generations timed",
+                   "l2": "per-generation working set (activations > 1 GB at 64 candidates) exceeds the 126 MB L2; no explicit flush",
+                   "parallelism": (f"population of {P_total} sharded over {world} ranks ({P_rank} candidates each), one "
+                                   f"fitness all-gather per generation") if world > 1 else "single GPU"},
+        "ms_per_generation": ms / gens,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * iters, "d2h_bytes_per_step": d2h * iters,
+                "ms_per_generation": ms_e2e / gens,
+                "what": "same loop; every generation re-uploads the input waveform + W from pinned host memory and reads "
+                        "fitness + embeddings back (per rank)"},
+        "gpu_launches": int(acc["launches"]),
         "clocks": clocks,
         "roofline": roofline,
+        "host_cma_ms_per_generation": acc["host_cma_ms"] / gens,
+        "comp_fallbacks": int(acc["comp_fallbacks"]), "act_overflow": int(acc["act_overflow"]),
         "wall_s": wall,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if shard_check is not None:
+        line["shard_check"] = shard_check
+    if world == 1 and not args.no_cpu_baseline and args.cpu_sample > 0:
         import torch as _t
 
-        plugins_o, D_o, model_o, te = cpu_setup(x, ["eq", "comp", "reverb"])
-        n = args.cpu_sample
-        Wc = np.random.RandomState(7).rand(n, D_o)
+        bias = (model.fc_mid.bias.detach().cpu().clone(), model.fc_side.bias.detach().cpu().clone())
+        plugins_o, D_o, model_o, te_o = cpu_setup(x, c["chain"], head_bias=bias)
+        keys = sorted(record)
+        n, dt, max_rel, argsort_equal, near_ties = 0, 0.0, 0.0, True, 0
+        for k in keys:  # the CPU leg re-scores populations the GPU evaluated inside the timed region
+            Wc, f_gpu = record[k]
+            t0 = time.perf_counter()
+            f_cpu = cpu_candidates(x, Wc, plugins_o, model_o, te_o).numpy()
+            dt += time.perf_counter() - t0
+            n += len(Wc)
+            max_rel = max(max_rel, float(np.max(np.abs(f_gpu - f_cpu) / np.maximum(np.abs(f_cpu), 1e-3))))
+            argsort_equal &= bool(np.array_equal(np.argsort(f_gpu, kind="stable"), np.argsort(f_cpu, kind="stable")))
+            near_ties += int(np.sum(np.diff(np.sort(f_cpu.astype(np.float64))) < 1e-6))
+        ns = min(len(record[keys[0]][0]), 16)
         t0 = time.perf_counter()
-        cpu_candidates(x, Wc, plugins_o, model_o, te)
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
-                                "sample": f"{n} candidates of the same workload: oracle DSP (C, one candidate per host thread) "
-                                          f"+ torch CPU Cnn14, {dt:.1f} s"}
+        cpu_candidates(x, record[keys[0]][0][:ns], plugins_o, model_o, te_o, serial=True)
+        value_serial = ns / (time.perf_counter() - t0)
+        line["cpu_baseline"] = {"value": n / dt, "value_serial": value_serial, "unit": UNIT,
+                                "cores": _t.get_num_threads(), "kind": "port",
+                                "sample": f"{n} candidates = the first {len(keys)} populations of the timed region: oracle DSP "
+                                          f"(C, one candidate per host thread) + torch CPU Cnn14, {dt:.1f} s; value_serial: "
+                                          f"{ns} candidates rendered one after the other (reference default branch)"}
+        line["parity"] = {"candidates": n, "max_rel_err": max_rel, "argsort_equal": argsort_equal,
+                          "near_ties_below_1e-6": near_ties,
+                          "what": "fitness of the populations timed on the GPU vs the CPU oracle on the same W; "
+                                  "rel err = |df| / max(|f|, 1e-3), gate 1e-4; argsort per population"}
     print(json.dumps(line))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pop", type=int, default=64)
-    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (default 2)")
+    ap.add_argument("--pop", type=int, default=None, help="total population (default: the config's)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --pop candidates PER GPU (default: sharded)")
+    ap.add_argument("--seconds", type=float, default=None)
+    ap.add_argument("--iters", type=int, default=None, help="generations per step (default: the config's ES length)")
+    ap.add_argument("--chain", default=None, choices=sorted(ORACLE_KINDS))
     ap.add_argument("--precision", type=int, default=None, help="0 = fp32 CUDA cores, 1 = fp16x3 tcgen05")
-    ap.add_argument("--cpu-sample", type=int, default=96,
-                    help="candidates timed for cpu_baseline in the default arm (about 10-30 s of host work)")
-    ap.add_argument("--ref-sample", type=int, default=16,
-                    help="candidates per step of the --impl reference arm (bounded sample of the P=64 population)")
+    ap.add_argument("--cpu-sample", type=int, default=2,
+                    help="populations of the timed region re-scored by the CPU oracle (cpu_baseline + parity)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 

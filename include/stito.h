@@ -14,8 +14,10 @@
  *     float64 on [0,1] exactly as pycma hands them to evaluate();
  *   - data pointers may be HOST or DEVICE pointers (detected with
  *     cudaPointerGetAttributes); the library never frees caller memory;
- *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream);
- *     calls that write to host memory return after the copy has completed;
+ *   - `stream` is a cudaStream_t passed as void*.  NULL = the handle's own (non-blocking) stream, which is NOT
+ *     ordered against the legacy default stream: callers whose device inputs are produced on the legacy default
+ *     stream pass cudaStreamLegacy ((void*)1), on a per-thread default stream cudaStreamPerThread ((void*)2).
+ *     Every call returns after its work on `stream` has completed (outputs are valid on return);
  *   - one handle = one host thread at a time (the reference's plugin objects are
  *     stateful and not re-entrant either, style_transfer.py:76-92).
  */
@@ -99,6 +101,11 @@ typedef struct {
     double encoder_flop;         /* 2*MACs of the 12 convolutions + heads                       */
     double dsp_bytes, frontend_bytes; /* algorithmic HBM bytes                      */
     float ms_conv[12];           /* per conv layer                                              */
+    /* -- appended in ABI 2.0.0 -- */
+    int32_t comp_fallbacks;      /* compressor super-blocks whose time-parallel Newton iteration did not converge
+                                    and were recomputed by the exact serial loop (results stay correct)          */
+    int32_t act_overflow;        /* 1: an activation left the fp16x3 range; the call was redone with precision 0
+                                    and the handle stays at precision 0                                          */
 } stito_timing;
 
 /* Create an evaluator for (chain, encoder) on CUDA device `device`.  `weights` may be NULL:

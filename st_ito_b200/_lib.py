@@ -64,6 +64,7 @@ class Timing(Structure):
         ("launches", c_int32), ("precision", c_int32),
         ("encoder_flop", c_double), ("dsp_bytes", c_double), ("frontend_bytes", c_double),
         ("ms_conv", c_float * 12),
+        ("comp_fallbacks", c_int32), ("act_overflow", c_int32),
     ]
 
 

@@ -254,7 +254,7 @@ constexpr size_t kCsSmem = (size_t)(kCsT * kCsPitch + 2 * kCsT + 2 * (kCsT / 32)
 
 __global__ void __launch_bounds__(kCsT, 1) compressor_scan_kernel(SigView in, const float *in_peak, float *out,
                                                                    int chs, int64_t L, const CompParams *prm,
-                                                                   unsigned *out_peak) {
+                                                                   unsigned *out_peak, int *noconv) {
     extern __shared__ float cs_sm[];
     float *xs = cs_sm;                       // [kCsT][kCsPitch] samples, later overwritten by the output
     float *sout_s = xs + kCsT * kCsPitch;    // [kCsT] outgoing state of each chunk
@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(kCsT, 1) compressor_scan_kernel(SigView in, co
         const int len = max(0, min(kCsC, nb - t * kCsC));
         float s_in = *carry_s;
 
+        bool converged = false;
         for (int it = 0; it < kCsMaxIter; ++it) {
             float env = s_in, slope = 1.0f;
             for (int j = 0; j < len; ++j) {
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kCsT, 1) compressor_scan_kernel(SigView in, co
             }
             const int all_tight = __syncthreads_and(tight);
             const int all_loose = __syncthreads_and(loose);
-            if (all_tight || (it >= 8 && all_loose)) break;
+            if (all_tight || (it >= 8 && all_loose)) { converged = true; break; }
             // inclusive scan of the affine maps (composition: later o earlier)
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -356,6 +357,29 @@ __global__ void __launch_bounds__(kCsT, 1) compressor_scan_kernel(SigView in, co
             __syncthreads();  // wM / wE / sout_s / slope_s are rewritten next iteration
         }
 
+        if (!converged) {
+            // The policy iteration is monotone and finite in exact arithmetic; in float32 a decision can keep flipping at
+            // rounding level.  Never hand out an unconverged state silently: thread 0 walks the super-block serially (the
+            // oracle's own loop, ~0.4 ms) and the event is counted in *noconv (stito_timing.comp_fallbacks).
+            __syncthreads();
+            if (t == 0) {
+                float env = *carry_s;
+                for (int tt = 0; tt < kCsT; ++tt) {
+                    sout_s[tt] = env;  // state entering chunk tt
+                    const float *r = xs + tt * kCsPitch;
+                    const int ln = max(0, min(kCsC, nb - tt * kCsC));
+                    for (int j = 0; j < ln; ++j) {
+                        const float a = fabsf(r[j]);
+                        const float d = __fsub_rn(env, a);
+                        env = __fadd_rn(a, (a > env) ? __fmul_rn(q.cte_at, d) : __fmul_rn(q.cte_rl, d));
+                    }
+                }
+                if (noconv != nullptr) atomicAdd(noconv, 1);
+            }
+            __syncthreads();
+            s_in = sout_s[t];
+            __syncthreads();
+        }
         // final pass: exact recurrence from the converged state + gain computer; output replaces the input row
         {
             float env = s_in;
@@ -908,9 +932,8 @@ cudaError_t launch_eq(cudaStream_t st, SigView in, const float *in_peak, float *
     eq_chunk_kernel<false><<<grid, 128, 0, st>>>(in, in_peak, nullptr, chs, L, K, coefs, scratch_f, nullptr);
     {
         constexpr int smem = kEqStates * kStitchTile * (int)sizeof(double);
-        // per-device attribute (a process may drive several GPUs): set on every launch, it is cheap
         {
-            cudaError_t e = cudaFuncSetAttribute(eq_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void *>(&eq_stitch_kernel), smem);
             if (e != cudaSuccess) return e;
         }
         eq_stitch_kernel<<<streams, kStitchThreads, smem, st>>>(chs, K, coefs, scratch_f, scratch_s);
@@ -921,14 +944,13 @@ cudaError_t launch_eq(cudaStream_t st, SigView in, const float *in_peak, float *
 }
 
 cudaError_t launch_compressor(cudaStream_t st, SigView in, const float *in_peak, float *out, int P,
-                              int chs, int64_t L, const CompParams *prm, unsigned *out_peak,
+                              int chs, int64_t L, const CompParams *prm, unsigned *out_peak, int *noconv,
                               int *launches) {
-    // per-device attribute (a process may drive several GPUs): set on every launch, it is cheap
     {
-        cudaError_t e = cudaFuncSetAttribute(compressor_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCsSmem);
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void *>(&compressor_scan_kernel), (int)kCsSmem);
         if (e != cudaSuccess) return e;
     }
-    compressor_scan_kernel<<<P * chs, kCsT, kCsSmem, st>>>(in, in_peak, out, chs, L, prm, out_peak);
+    compressor_scan_kernel<<<P * chs, kCsT, kCsSmem, st>>>(in, in_peak, out, chs, L, prm, out_peak, noconv);
     *launches += 1;
     return cudaGetLastError();
 }
@@ -1005,7 +1027,7 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
         const bool pair = stereo != 0;
         Kern kern = pair ? (seg == kRevMaxSegF ? reverb_core_kernel<kRevMaxSegF, true> : reverb_core_kernel<32, true>)
                          : (seg == kRevMaxSegF ? reverb_core_kernel<kRevMaxSegF, false> : reverb_core_kernel<32, false>);
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = ensure_dyn_smem(reinterpret_cast<const void *>(kern), (int)smem);
         if (e != cudaSuccess) return e;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(P * chs);
@@ -1027,11 +1049,11 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
     const size_t smem = (size_t)(g.total + g.block) * sizeof(float);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (stereo) {
-        e = cudaFuncSetAttribute(reverb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = ensure_dyn_smem(reinterpret_cast<const void *>(&reverb_kernel<2>), (int)smem);
         if (e != cudaSuccess) return e;
         reverb_kernel<2><<<P, 512, smem, st>>>(in, in_peak, out, 2, L, g, prm, out_peak);
     } else {
-        e = cudaFuncSetAttribute(reverb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = ensure_dyn_smem(reinterpret_cast<const void *>(&reverb_kernel<1>), (int)smem);
         if (e != cudaSuccess) return e;
         reverb_kernel<1><<<P * chs, 256, smem, st>>>(in, in_peak, out, chs, L, g, prm, out_peak);
     }

@@ -23,7 +23,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <map>
 #include <string>
+#include <utility>
 
 #include "encoder_tc.h"
 
@@ -149,6 +152,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 }
 
 constexpr float kActScale = 64.0f;  // activations are stored as fp16 hi/lo of (value * 2^6)
+constexpr float kHalfMax = 65504.0f;
 
 struct ConvTcParams {
     const float *bias;   // [Cout]
@@ -168,6 +172,9 @@ struct ConvTcParams {
     // Compensation of the tensor core's truncating fp32 accumulate: every drained chunk partial sum is multiplied by
     // 1 + trunc_comp * (number of K = 16 MMA steps accumulated into it); see chunk_comp().
     float trunc_comp;
+    // fp16 range guard: activations are stored as fp16 pairs of (value * 2^6); anything above kHalfMax is clamped and
+    // *overflow (device int, nullable) is raised so that the caller can redo the evaluation with the fp32 encoder.
+    int *overflow;
 };
 
 constexpr int kTileM = 128;
@@ -226,6 +233,13 @@ __device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&
             dst[1] = make_float4(y[4], y[5], y[6], y[7]);
         } else {
             uint32_t hi[4], lo[4];
+            bool ovf = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // post-ReLU: only the upper bound can be hit (NaN compares false and passes through)
+                ovf |= y[j] > kHalfMax;
+                y[j] = fminf(y[j], kHalfMax);
+            }
+            if (ovf && p.overflow != nullptr) atomicOr(p.overflow, 1);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const __half h0v = __float2half_rn(y[2 * j]), h1v = __float2half_rn(y[2 * j + 1]);
@@ -662,7 +676,8 @@ __global__ void __launch_bounds__(256) wino_in_kernel(const __half *__restrict__
 __global__ void __launch_bounds__(256) wino_out_kernel(const float *__restrict__ M, const float *__restrict__ bias,
                                                        float unscale, __half *__restrict__ out_hi,
                                                        __half *__restrict__ out_lo, float *__restrict__ out_f32, int N,
-                                                       int H, int W, int Cout, int th, int tw, int Tp, int pool) {
+                                                       int H, int W, int Cout, int th, int tw, int Tp, int pool,
+                                                       int *__restrict__ overflow) {
     const int C2 = Cout >> 1;
     const int64_t total = (int64_t)N * th * tw * C2;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -697,8 +712,10 @@ __global__ void __launch_bounds__(256) wino_out_kernel(const float *__restrict__
             if (ty >= Ho || tx >= Wo) continue;
             float o[2];
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch)
+            for (int ch = 0; ch < 2; ++ch) {
                 o[ch] = ((y[0][0][ch] + y[0][1][ch]) + (y[1][0][ch] + y[1][1][ch])) * (0.25f * kActScale);
+                if (o[ch] > kHalfMax) { o[ch] = kHalfMax; if (overflow != nullptr) atomicOr(overflow, 1); }
+            }
             const size_t oo = (((size_t)n * Ho + ty) * Wo + tx) * Cout + 2 * c2;
             const __half h0 = __float2half_rn(o[0]), h1 = __float2half_rn(o[1]);
             *reinterpret_cast<__half2 *>(out_hi + oo) = __halves2half2(h0, h1);
@@ -715,7 +732,11 @@ __global__ void __launch_bounds__(256) wino_out_kernel(const float *__restrict__
                     if (out_f32 != nullptr) {
                         *reinterpret_cast<float2 *>(out_f32 + oo) = make_float2(y[i][j][0], y[i][j][1]);
                     } else {
-                        const float a = y[i][j][0] * kActScale, b = y[i][j][1] * kActScale;
+                        float a = y[i][j][0] * kActScale, b = y[i][j][1] * kActScale;
+                        if (a > kHalfMax || b > kHalfMax) {
+                            a = fminf(a, kHalfMax); b = fminf(b, kHalfMax);
+                            if (overflow != nullptr) atomicOr(overflow, 1);
+                        }
                         const __half h0 = __float2half_rn(a), h1 = __float2half_rn(b);
                         *reinterpret_cast<__half2 *>(out_hi + oo) = __halves2half2(h0, h1);
                         *reinterpret_cast<__half2 *>(out_lo + oo) = __halves2half2(__float2half_rn(a - __half2float(h0)),
@@ -734,7 +755,8 @@ __global__ void __launch_bounds__(256) wino_out_kernel(const float *__restrict__
 constexpr int kC1Px = 4;
 __global__ void __launch_bounds__(256) tc_conv_first_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                             const float *__restrict__ bias, __half *__restrict__ yh,
-                                                            __half *__restrict__ yl, int N, int H, int W) {
+                                                            __half *__restrict__ yl, int N, int H, int W,
+                                                            int *__restrict__ overflow) {
     const int g = threadIdx.x & 7;
     float wr[9][8], br[8];
 #pragma unroll
@@ -780,6 +802,10 @@ __global__ void __launch_bounds__(256) tc_conv_first_kernel(const float *__restr
                     }
                 a0 = fmaxf(a0 + br[2 * c2], 0.f) * kActScale;
                 a1 = fmaxf(a1 + br[2 * c2 + 1], 0.f) * kActScale;
+                if (a0 > kHalfMax || a1 > kHalfMax) {
+                    a0 = fminf(a0, kHalfMax); a1 = fminf(a1, kHalfMax);
+                    if (overflow != nullptr) atomicOr(overflow, 1);
+                }
                 const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
                 const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
                 hi[c2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
@@ -814,11 +840,52 @@ int tc_fail(const char *what, const char *detail) {
     return -1;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): done once each, not per launch
+// (a generation used to make ~25 of these driver calls).
+}  // namespace
+cudaError_t ensure_dyn_smem(const void *func, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> done;  // (kernel, device) -> bytes granted so far
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find({func, dev});
+    if (it != done.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done[{func, dev}] = bytes;
+    return e;
+}
+namespace {
+
+const CUtensorMap *cached_map(TcWorkspace &ws, const TcMapKey &key, bool *hit) {
+    for (TcMapEntry *e : ws.maps)
+        if (e->key == key) { *hit = true; return reinterpret_cast<const CUtensorMap *>(e->map); }
+    if (ws.maps.size() >= 1024) {  // unbounded shape churn: start over
+        for (TcMapEntry *e : ws.maps) delete e;
+        ws.maps.clear();
+    }
+    TcMapEntry *e = new TcMapEntry();
+    e->key = key;
+    ws.maps.push_back(e);
+    *hit = false;
+    return reinterpret_cast<const CUtensorMap *>(e->map);
+}
+void drop_last_map(TcWorkspace &ws) {
+    delete ws.maps.back();
+    ws.maps.pop_back();
+}
+
 // activations: fp16 NHWC viewed as 4-D (C, W, H, N), box (64, BW, BH, IPT), 128B swizzle, zero OOB fill
-int make_act_map(CUtensorMap *m, const void *base, int N, int H, int W, int C, int BW, int BH, int IPT,
-                 int slabk = kSlabK) {
+const CUtensorMap *make_act_map(TcWorkspace &ws, const void *base, int N, int H, int W, int C, int BW, int BH, int IPT,
+                                int slabk = kSlabK) {
+    const TcMapKey key{base, {N, H, W, C}, {slabk, BW, BH, IPT}};
+    bool hit = false;
+    const CUtensorMap *cm = cached_map(ws, key, &hit);
+    if (hit) return cm;
+    CUtensorMap *m = const_cast<CUtensorMap *>(cm);
     EncodeTiledFn enc = get_encode();
-    if (!enc) return tc_fail("cuTensorMapEncodeTiled", "driver entry point not found");
+    if (!enc) { drop_last_map(ws); tc_fail("cuTensorMapEncodeTiled", "driver entry point not found"); return nullptr; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)slabk, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)IPT};
@@ -830,15 +897,22 @@ int make_act_map(CUtensorMap *m, const void *base, int N, int H, int W, int C, i
     if (r != CUDA_SUCCESS) {
         char buf[160];
         snprintf(buf, sizeof(buf), "CUresult %d for activation map N=%d H=%d W=%d C=%d box=(64,%d,%d,%d)", (int)r, N, H, W, C, BW, BH, IPT);
-        return tc_fail("cuTensorMapEncodeTiled", buf);
+        drop_last_map(ws);
+        tc_fail("cuTensorMapEncodeTiled", buf);
+        return nullptr;
     }
-    return 0;
+    return cm;
 }
 
 // weights: fp16 [Cout][K] K-major, box (64, BN)
-int make_w_map(CUtensorMap *m, const void *base, int Cout, int K, int BN, int slabk = kSlabK) {
+const CUtensorMap *make_w_map(TcWorkspace &ws, const void *base, int Cout, int K, int BN, int slabk = kSlabK) {
+    const TcMapKey key{base, {Cout, K, 0, 0}, {slabk, BN, 0, 0}};
+    bool hit = false;
+    const CUtensorMap *cm = cached_map(ws, key, &hit);
+    if (hit) return cm;
+    CUtensorMap *m = const_cast<CUtensorMap *>(cm);
     EncodeTiledFn enc = get_encode();
-    if (!enc) return tc_fail("cuTensorMapEncodeTiled", "driver entry point not found");
+    if (!enc) { drop_last_map(ws); tc_fail("cuTensorMapEncodeTiled", "driver entry point not found"); return nullptr; }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)slabk, (cuuint32_t)BN};
@@ -850,9 +924,11 @@ int make_w_map(CUtensorMap *m, const void *base, int Cout, int K, int BN, int sl
     if (r != CUDA_SUCCESS) {
         char buf[128];
         snprintf(buf, sizeof(buf), "CUresult %d for weight map Cout=%d K=%d BN=%d", (int)r, Cout, K, BN);
-        return tc_fail("cuTensorMapEncodeTiled", buf);
+        drop_last_map(ws);
+        tc_fail("cuTensorMapEncodeTiled", buf);
+        return nullptr;
     }
-    return 0;
+    return cm;
 }
 
 int num_sms() {
@@ -869,9 +945,8 @@ template <int BN, int STAGES, int SLABK, int MT = 1>
 int launch_conv_tc_t(cudaStream_t st, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh,
                      const CUtensorMap &bl, const ConvTcParams &p) {
     constexpr int smem = STAGES * (MT * 2 * kTileM * SLABK * 2 + 2 * BN * SLABK * 2) + 1024 + 256 + 2048 * 4;  // ring, align, barriers, bias
-    // per-device attribute (a process may drive several GPUs): set on every launch, it is cheap
     {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES, SLABK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void *>(&conv3x3_tc_kernel<BN, STAGES, SLABK, MT>), smem);
         if (e != cudaSuccess) return tc_fail("cudaFuncSetAttribute", cudaGetErrorString(e));
     }
     const int total = ((p.mtiles + MT - 1) / MT) * p.ntiles * (p.gemm ? 16 : 1);
@@ -1056,6 +1131,8 @@ int tc_prepare_layer(const float *wf, int cin, int cout, ConvLayer *cl, std::vec
 }
 
 void tc_workspace_release(TcWorkspace *ws) {
+    for (TcMapEntry *e : ws->maps) delete e;
+    ws->maps.clear();
     for (int i = 0; i < TcWorkspace::kBufs; ++i) {
         if (ws->buf[i]) cudaFree(ws->buf[i]);
         ws->buf[i] = nullptr;
@@ -1064,13 +1141,14 @@ void tc_workspace_release(TcWorkspace *ws) {
 }
 
 // One conv layer on tensor cores: in (hi, lo) NHWC [N][H][W][Cin] -> out fp16 pair or fp32.
-static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, const __half *in_lo, __half *out_hi,
-                   __half *out_lo, float *out_f32, int N, int H, int W, bool pool, int *launches) {
+static int conv_tc(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, const __half *in_hi, const __half *in_lo,
+                   __half *out_hi, __half *out_lo, float *out_f32, int N, int H, int W, bool pool, int *launches) {
     ConvTcParams p{};
     p.bias = l.bias; p.unscale = l.w_unscale / kActScale;
     p.out_scale = out_f32 ? 1.0f : (pool ? 0.25f * kActScale : kActScale);  // exact powers of two
     p.pool = pool ? 1 : 0;
     p.trunc_comp = chunk_comp();
+    p.overflow = ws.overflow_flag;
     p.out_hi = out_hi; p.out_lo = out_lo; p.out_f32 = out_f32;
     p.N = N; p.H = H; p.W = W; p.Cin = l.cin; p.Cout = l.cout;
     p.BW = W < 64 ? W : 64;
@@ -1092,20 +1170,19 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, con
     p.chunk_slabs = chunk_slabs();
     if (l.cin % kSlabK != 0 || l.cout % BN != 0 || l.cout > 2048 || (BN != 64 && BN != 128 && BN != 256))
         return tc_fail("conv_tc", "unsupported channel counts");
-    CUtensorMap ah, al, bh_, bl;
+    const CUtensorMap *ah, *al, *bh_, *bl;
     if (l.cin == 64 && l.cout == 64 && p.BW == 16 && p.BH == 8 && p.IPT == 1 && use_c64()) {
         // resident weights + kh-shared A boxes (conv3x3_c64_kernel)
-        if (make_act_map(&ah, in_hi, N, H, W, 64, 16, kC64BoxRows, 1)) return -1;
-        if (make_act_map(&al, in_lo, N, H, W, 64, 16, kC64BoxRows, 1)) return -1;
-        if (make_w_map(&bh_, l.w_hi, 64, 9 * 64, 64)) return -1;
-        if (make_w_map(&bl, l.w_lo, 64, 9 * 64, 64)) return -1;
-        // per-device attribute (a process may drive several GPUs): set on every launch, it is cheap
+        if (!(ah = make_act_map(ws, in_hi, N, H, W, 64, 16, kC64BoxRows, 1))) return -1;
+        if (!(al = make_act_map(ws, in_lo, N, H, W, 64, 16, kC64BoxRows, 1))) return -1;
+        if (!(bh_ = make_w_map(ws, l.w_hi, 64, 9 * 64, 64))) return -1;
+        if (!(bl = make_w_map(ws, l.w_lo, 64, 9 * 64, 64))) return -1;
         {
-            cudaError_t e = cudaFuncSetAttribute(conv3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC64Smem);
+            cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void *>(&conv3x3_c64_kernel), kC64Smem);
             if (e != cudaSuccess) return tc_fail("cudaFuncSetAttribute", cudaGetErrorString(e));
         }
         const int grid = p.mtiles < num_sms() ? p.mtiles : num_sms();
-        conv3x3_c64_kernel<<<grid, kConvThreads, kC64Smem, st>>>(ah, al, bh_, bl, p);
+        conv3x3_c64_kernel<<<grid, kConvThreads, kC64Smem, st>>>(*ah, *al, *bh_, *bl, p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return tc_fail("conv3x3_c64_kernel launch", cudaGetErrorString(e));
         *launches += 1;
@@ -1115,20 +1192,20 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, const __half *in_hi, con
     // further ahead of the MMA issuer) or 64 (128-byte swizzle), chosen per layer; STITO_TC_SLABK overrides
     const int slabk = slab_k(l.cin);
     p.chunk_slabs = chunk_slabs() * (64 / slabk);
-    if (make_act_map(&ah, in_hi, N, H, W, l.cin, p.BW, p.BH, p.IPT, slabk)) return -1;
-    if (make_act_map(&al, in_lo, N, H, W, l.cin, p.BW, p.BH, p.IPT, slabk)) return -1;
-    if (make_w_map(&bh_, l.w_hi, l.cout, 9 * l.cin, BN, slabk)) return -1;
-    if (make_w_map(&bl, l.w_lo, l.cout, 9 * l.cin, BN, slabk)) return -1;
+    if (!(ah = make_act_map(ws, in_hi, N, H, W, l.cin, p.BW, p.BH, p.IPT, slabk))) return -1;
+    if (!(al = make_act_map(ws, in_lo, N, H, W, l.cin, p.BW, p.BH, p.IPT, slabk))) return -1;
+    if (!(bh_ = make_w_map(ws, l.w_hi, l.cout, 9 * l.cin, BN, slabk))) return -1;
+    if (!(bl = make_w_map(ws, l.w_lo, l.cout, 9 * l.cin, BN, slabk))) return -1;
     int rc;
     if (slabk == 32) {
-        if (BN == 64) rc = launch_conv_tc_t<64, 8, 32>(st, ah, al, bh_, bl, p);
-        else if (BN == 128) rc = launch_conv_tc_t<128, 6, 32>(st, ah, al, bh_, bl, p);
-        else rc = launch_conv_tc_t<256, 4, 32>(st, ah, al, bh_, bl, p);
+        if (BN == 64) rc = launch_conv_tc_t<64, 8, 32>(st, *ah, *al, *bh_, *bl, p);
+        else if (BN == 128) rc = launch_conv_tc_t<128, 6, 32>(st, *ah, *al, *bh_, *bl, p);
+        else rc = launch_conv_tc_t<256, 4, 32>(st, *ah, *al, *bh_, *bl, p);
     } else {
-        if (BN == 64) rc = launch_conv_tc_t<64, 4, 64>(st, ah, al, bh_, bl, p);
-        else if (BN == 128 && l.cin >= 128 && use_mt2()) rc = launch_conv_tc_t<128, 2, 64, 2>(st, ah, al, bh_, bl, p);  // 2 M tiles share B (-4.5 % on b2c2; b2c1, K = 576, prefers the deeper 3-stage ring)
-        else if (BN == 128) rc = launch_conv_tc_t<128, 3, 64>(st, ah, al, bh_, bl, p);
-        else rc = launch_conv_tc_t<256, 2, 64>(st, ah, al, bh_, bl, p);
+        if (BN == 64) rc = launch_conv_tc_t<64, 4, 64>(st, *ah, *al, *bh_, *bl, p);
+        else if (BN == 128 && l.cin >= 128 && use_mt2()) rc = launch_conv_tc_t<128, 2, 64, 2>(st, *ah, *al, *bh_, *bl, p);  // 2 M tiles share B (-4.5 % on b2c2; b2c1, K = 576, prefers the deeper 3-stage ring)
+        else if (BN == 128) rc = launch_conv_tc_t<128, 3, 64>(st, *ah, *al, *bh_, *bl, p);
+        else rc = launch_conv_tc_t<256, 2, 64>(st, *ah, *al, *bh_, *bl, p);
     }
     if (rc == 0) *launches += 1;
     return rc;
@@ -1158,16 +1235,16 @@ static int conv_wino(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, const
     p.unscale = 1.0f; p.out_scale = 1.0f;
     const int slabk = slab_k(l.cin);
     p.chunk_slabs = chunk_slabs() * (64 / slabk);
-    CUtensorMap ah, al, bh_, bl;
-    if (make_w_map(&ah, v_hi, 16 * Tp, l.cin, kTileM, slabk)) return -1;   // V as [16 * Tp][Cin], box (K slab, 128 rows)
-    if (make_w_map(&al, v_lo, 16 * Tp, l.cin, kTileM, slabk)) return -1;
-    if (make_w_map(&bh_, l.u_hi, 16 * l.cout, l.cin, 256, slabk)) return -1;
-    if (make_w_map(&bl, l.u_lo, 16 * l.cout, l.cin, 256, slabk)) return -1;
-    int rc = slabk == 32 ? launch_conv_tc_t<256, 4, 32>(st, ah, al, bh_, bl, p) : launch_conv_tc_t<256, 2, 64>(st, ah, al, bh_, bl, p);
+    const CUtensorMap *ah, *al, *bh_, *bl;
+    if (!(ah = make_w_map(ws, v_hi, 16 * Tp, l.cin, kTileM, slabk))) return -1;   // V as [16 * Tp][Cin], box (K slab, 128 rows)
+    if (!(al = make_w_map(ws, v_lo, 16 * Tp, l.cin, kTileM, slabk))) return -1;
+    if (!(bh_ = make_w_map(ws, l.u_hi, 16 * l.cout, l.cin, 256, slabk))) return -1;
+    if (!(bl = make_w_map(ws, l.u_lo, 16 * l.cout, l.cin, 256, slabk))) return -1;
+    int rc = slabk == 32 ? launch_conv_tc_t<256, 4, 32>(st, *ah, *al, *bh_, *bl, p) : launch_conv_tc_t<256, 2, 64>(st, *ah, *al, *bh_, *bl, p);
     if (rc) return rc;
     const float unscale = l.u_unscale / (kActScale * kWinoVScale);
     wino_out_kernel<<<blocks_for((int64_t)T * (l.cout / 2), 256), 256, 0, st>>>(M, l.bias, unscale, out_hi, out_lo, out_f32, N, H, W,
-                                                                                  l.cout, th, tw, Tp, pool ? 1 : 0);
+                                                                                  l.cout, th, tw, Tp, pool ? 1 : 0, ws.overflow_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tc_fail("winograd transform launch", cudaGetErrorString(e));
     *launches += 3;
@@ -1192,25 +1269,25 @@ int tc_encoder_forward(cudaStream_t st, const EncoderDev &enc, TcWorkspace &ws, 
         if (ev) cudaEventRecord(ev[2 * b], st);
         if (b == 0) {
             if ((uint64_t)px >= (1ull << 31)) return tc_fail("tc_encoder_forward", "micro-batch too large for 32-bit pixel indices");
-            tc_conv_first_kernel<<<blocks_for((int64_t)px * 8 / kC1Px, 256), 256, 0, st>>>(feat, l1.w, l1.bias, m_hi, m_lo, N, H, W);
+            tc_conv_first_kernel<<<blocks_for((int64_t)px * 8 / kC1Px, 256), 256, 0, st>>>(feat, l1.w, l1.bias, m_hi, m_lo, N, H, W, ws.overflow_flag);
             *launches += 1;
         } else {
             if (wino_layer(l1) && use_wino()) {
                 if (conv_wino(st, l1, ws, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
-            } else if (conv_tc(st, l1, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
+            } else if (conv_tc(st, l1, ws, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
         }
         if (ev) cudaEventRecord(ev[2 * b + 1], st);
         const bool wino2 = wino_layer(l2) && use_wino();
         if (b < 5) {  // conv2 + ReLU + 2x2 average pool + hi/lo split in one kernel -> next block's input
             if (wino2) {
                 if (conv_wino(st, l2, ws, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
-            } else if (conv_tc(st, l2, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
+            } else if (conv_tc(st, l2, ws, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
             H /= 2;
             W /= 2;
         } else {
             if (wino2) {
                 if (conv_wino(st, l2, ws, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, false, launches)) return -1;
-            } else if (conv_tc(st, l2, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, false, launches)) return -1;
+            } else if (conv_tc(st, l2, ws, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, false, launches)) return -1;
         }
     }
     if (ev) cudaEventRecord(ev[12], st);

@@ -8,10 +8,31 @@
 
 namespace stito {
 
+// CUtensorMap descriptors are pure functions of (base pointer, geometry, box): the workspace buffers and the
+// weights do not move between generations, so every descriptor is encoded once and looked up afterwards
+// (cuTensorMapEncodeTiled is a driver call; a generation used to make ~76 of them).
+struct TcMapKey {
+    const void *base;
+    int dims[4];   // activation map: N, H, W, C; weight map: Cout, K, 0, 0
+    int box[4];    // activation map: slabk, BW, BH, IPT; weight map: slabk, BN, 0, 0
+    bool operator==(const TcMapKey &o) const {
+        if (base != o.base) return false;
+        for (int i = 0; i < 4; ++i)
+            if (dims[i] != o.dims[i] || box[i] != o.box[i]) return false;
+        return true;
+    }
+};
+struct alignas(64) TcMapEntry {
+    unsigned char map[128];  // CUtensorMap (128 bytes, 64-byte aligned)
+    TcMapKey key;
+};
+
 struct TcWorkspace {
     static constexpr int kBufs = 7;  // 0-3: activations (see tc_encoder_forward), 4-6: Winograd V_hi, V_lo, M
     void *buf[kBufs] = {};
     size_t cap[kBufs] = {};
+    std::vector<TcMapEntry *> maps;  // descriptor cache (cleared whenever a buffer is reallocated)
+    int *overflow_flag = nullptr;    // device int: set when an activation exceeded the fp16 range (see store_tile)
 };
 
 // true when the tcgen05 encoder is compiled in and enabled

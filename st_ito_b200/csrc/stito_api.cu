@@ -172,7 +172,11 @@ struct stito_handle {
 
     // work buffers
     DevBuf audio[2], eq_f, eq_s, params, peaks, Wdev, feat, act[3], pooled, emb, fit, flags, xin;
-    HostBuf hparams, hW;
+    HostBuf hparams, hW, hflags;
+    // flags (device ints): [0], [1] NaN in mid / side embeddings; [2] an activation left the fp16 range of the fp16x3
+    // encoder; [3] compressor super-blocks redone serially (Newton iteration did not converge)
+    bool warned_overflow = false;
+    int comp_fallbacks_total = 0;
     ReverbGeom rgeom{};
     TcWorkspace tcws;
 
@@ -352,7 +356,8 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
                 break;
             }
             case STITO_FX_COMPRESSOR:
-                CU(launch_compressor(st, cur, in_peak, out, P, cur_chs, L, reinterpret_cast<const CompParams *>(slot), opk, launches));
+                CU(launch_compressor(st, cur, in_peak, out, P, cur_chs, L, reinterpret_cast<const CompParams *>(slot), opk,
+                                     h->flags.as<int>() + 3, launches));
                 break;
             case STITO_FX_DISTORTION:
                 CU(launch_distortion(st, cur, in_peak, out, P, cur_chs, L, reinterpret_cast<const DistParams *>(slot), opk, launches));
@@ -439,7 +444,7 @@ double encoder_flops(int N, int T, int mel) {
 extern "C" {
 
 const char *stito_last_error(void) { return g_err.c_str(); }
-int stito_version(void) { return 100; }
+int stito_version(void) { return 200; }
 
 int stito_create(const stito_chain_desc *chain, const stito_encoder_weights *wts, int device,
                  stito_handle **out) {
@@ -474,6 +479,9 @@ int stito_create(const stito_chain_desc *chain, const stito_encoder_weights *wts
     for (int i = 0; i < kNumEvents; ++i) CUB(cudaEventCreate(&h->ev[i]));
     for (int i = 0; i < 13; ++i) CUB(cudaEventCreate(&h->ev_conv[i]));
     CUB(h->flags.ensure(4 * sizeof(int)));
+    CUB(cudaMemset(h->flags.p, 0, 4 * sizeof(int)));
+    CUB(h->hflags.ensure(4 * sizeof(int)));
+    h->tcws.overflow_flag = h->flags.as<int>() + 2;
 
     if (wts) {
         if (wts->n_fft != 2048 || wts->hop <= 0 || wts->n_mels != 128 || wts->embed_dim <= 0 ||
@@ -565,6 +573,7 @@ void stito_destroy(stito_handle *h) {
     for (DevBuf *b : bufs) b->release();
     h->hparams.release();
     h->hW.release();
+    h->hflags.release();
     tc_workspace_release(&h->tcws);
     for (int i = 0; i < kNumEvents; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 13; ++i) if (h->ev_conv[i]) cudaEventDestroy(h->ev_conv[i]);
@@ -657,20 +666,10 @@ static int fetch_W(stito_handle *h, const double *W, int P, int D, cudaStream_t 
     return STITO_OK;
 }
 
-int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_t start, int64_t len,
-                          float *fitness, float *embeds, float *audio, void *stream) {
-    if (!h || !W) return fail(STITO_EINVAL, "NULL argument");
-    if (P <= 0) return fail(STITO_EINVAL, "empty population");
-    if (D != h->chain.num_w) return fail(STITO_EINVAL, "parameter vectors have %d entries, chain expects %d", D, h->chain.num_w);
-    if (h->in_chs == 0) return fail(STITO_ESTATE, "stito_set_input has not been called");
-    if (!h->has_encoder) return fail(STITO_ESTATE, "handle was created without encoder weights");
-    if (fitness && !h->has_target) return fail(STITO_ESTATE, "no target set (stito_set_target / stito_set_target_embeds)");
-    if (start < 0 || len <= 0 || start + len > h->in_cap) return fail(STITO_EINVAL, "view [%lld, %lld) outside the padded input of %lld samples", (long long)start, (long long)(start + len), (long long)h->in_cap);
-    CU(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->own_stream;
-    const double *Wh = nullptr;
-    int rc = fetch_W(h, W, P, D, st, &Wh);
-    if (rc) return rc;
+// One pass of evaluate() over the population, enqueued on `st` (no synchronisation): chain -> log-mel -> encoder
+// (h->precision) -> normalise -> fitness, results copied to the caller's buffers, flags [2], [3] to h->hflags.
+static int enqueue_population(stito_handle *h, cudaStream_t st, const double *Wh, int P, int D, int64_t start,
+                              int64_t len, float *fitness, float *embeds, float *audio, int *launches_out) {
     const int E = h->embed_dim;
     const int chs = h->in_chs;
     const int ochs = out_channels(h->chain, chs);
@@ -679,6 +678,7 @@ int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_
     float *mid_all = h->emb.as<float>(), *side_all = mid_all + (size_t)P * E;
     int launches = 0;
     SigView in{h->input.as<float>() + start, 0, h->in_cap};
+    CU(cudaMemsetAsync(h->flags.as<int>() + 2, 0, 2 * sizeof(int), st));
     CU(cudaEventRecord(h->ev[0], st));
     for (int p0 = 0; p0 < P; p0 += h->microbatch) {
         const int pb = (P - p0) < h->microbatch ? (P - p0) : h->microbatch;
@@ -686,7 +686,7 @@ int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_
         const float *y = nullptr;
         const unsigned *pk = nullptr;
         int ych = 0;
-        rc = run_chain(h, st, in, chs, len, Wh + (size_t)p0 * D, pb, D, &y, &pk, &ych, &launches);
+        int rc = run_chain(h, st, in, chs, len, Wh + (size_t)p0 * D, pb, D, &y, &pk, &ych, &launches);
         if (rc) return rc;
         if (tl) CU(cudaEventRecord(h->ev[1], st));
         if (audio) {
@@ -712,7 +712,56 @@ int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_
     CU(cudaEventRecord(h->ev[6], st));
     if (fitness) CU(cudaMemcpyAsync(fitness, h->fit.p, (size_t)P * sizeof(float), cudaMemcpyDefault, st));
     if (embeds) CU(cudaMemcpyAsync(embeds, h->emb.p, (size_t)2 * P * E * sizeof(float), cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(h->hflags.p, h->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    *launches_out += launches;
+    return STITO_OK;
+}
+
+int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_t start, int64_t len,
+                          float *fitness, float *embeds, float *audio, void *stream) {
+    if (!h || (!W && P > 0)) return fail(STITO_EINVAL, "NULL argument");
+    if (P < 0) return fail(STITO_EINVAL, "negative population size");
+    if (D != h->chain.num_w) return fail(STITO_EINVAL, "parameter vectors have %d entries, chain expects %d", D, h->chain.num_w);
+    if (h->in_chs == 0) return fail(STITO_ESTATE, "stito_set_input has not been called");
+    if (!h->has_encoder) return fail(STITO_ESTATE, "handle was created without encoder weights");
+    if (fitness && !h->has_target) return fail(STITO_ESTATE, "no target set (stito_set_target / stito_set_target_embeds)");
+    if (start < 0 || len <= 0 || start + len > h->in_cap) return fail(STITO_EINVAL, "view [%lld, %lld) outside the padded input of %lld samples", (long long)start, (long long)(start + len), (long long)h->in_cap);
+    if (P == 0) {  // an empty shard of a sharded population (more ranks than candidates): nothing to do, nothing written
+        memset(&h->timing, 0, sizeof(h->timing));
+        h->timing.precision = h->precision;
+        return STITO_OK;
+    }
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->own_stream;
+    const double *Wh = nullptr;
+    int rc = fetch_W(h, W, P, D, st, &Wh);
+    if (rc) return rc;
+    const int chs = h->in_chs;
+    const int ochs = out_channels(h->chain, chs);
+    int launches = 0;
+    rc = enqueue_population(h, st, Wh, P, D, start, len, fitness, embeds, audio, &launches);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(st));
+    const int *hf = h->hflags.as<int>();
+    int comp_fallbacks = hf[3];
+    int overflowed = 0;
+    if (hf[2] != 0 && h->precision == 1) {
+        // An activation exceeded what the fp16 hi/lo pairs of the tensor-core path can hold (|value| > 1023.5 after a
+        // ReLU): the result above is clamped, i.e. wrong.  Redo the evaluation with the fp32 CUDA-core encoder and keep
+        // the handle there (a checkpoint with such BatchNorm scales would trip on every generation).
+        if (!h->warned_overflow) {
+            fprintf(stderr, "libstito: activations exceed the fp16x3 range of the tensor-core encoder; this handle now uses "
+                            "the fp32 CUDA-core encoder (stito_set_precision(h, 1) to switch back)\n");
+            h->warned_overflow = true;
+        }
+        h->precision = 0;
+        overflowed = 1;
+        rc = enqueue_population(h, st, Wh, P, D, start, len, fitness, embeds, audio, &launches);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(st));
+        comp_fallbacks = hf[3];
+    }
+    h->comp_fallbacks_total += comp_fallbacks;
     // timing of this call
     stito_timing &t = h->timing;
     memset(&t, 0, sizeof(t));
@@ -731,6 +780,8 @@ int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_
     cudaGetLastError();
     t.launches = launches;
     t.precision = h->precision;
+    t.comp_fallbacks = comp_fallbacks;
+    t.act_overflow = overflowed;
     const int T = (int)(len / h->hop) + 1;
     t.encoder_flop = encoder_flops(P * ochs, T, h->n_mels);
     t.dsp_bytes = 4.0 * chs * len + 4.0 * ochs * len * P;

@@ -16,6 +16,9 @@ struct SigView {
     int64_t stride_c;
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), once per (kernel, device) (encoder_tc.cu)
+cudaError_t ensure_dyn_smem(const void *func, int bytes);
+
 // ---------------------------------------------------------------- DSP (dsp_kernels.cu)
 constexpr int kEqChunk = 512;  // samples per time-chunk of the chunk-parallel biquad cascade
 constexpr int kEqStates = 12;  // 6 biquads x 2 DF-II-transposed states
@@ -38,8 +41,9 @@ cudaError_t launch_eq(cudaStream_t st, SigView in, const float *in_peak, float *
                       double *scratch_s, unsigned *out_peak, int *launches);
 size_t eq_scratch_doubles(int P, int chs, int64_t L);  // per scratch buffer
 
+// *noconv (nullable, device) counts super-blocks whose Newton iteration did not converge and were redone serially
 cudaError_t launch_compressor(cudaStream_t st, SigView in, const float *in_peak, float *out, int P,
-                              int chs, int64_t L, const CompParams *prm, unsigned *out_peak,
+                              int chs, int64_t L, const CompParams *prm, unsigned *out_peak, int *noconv,
                               int *launches);
 cudaError_t launch_distortion(cudaStream_t st, SigView in, const float *in_peak, float *out, int P,
                               int chs, int64_t L, const DistParams *prm, unsigned *out_peak,

@@ -19,6 +19,15 @@ def world():
     return 0, 1
 
 
+def backend() -> str:
+    """Backend name of the default process group ("nccl", "gloo"), "" when not initialised."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return str(dist.get_backend())
+    return ""
+
+
 def shard_bounds(P: int, world_size: int, rank: int):
     """Contiguous slice [lo, hi) of a population of P owned by `rank`; chunk = ceil(P / world)."""
     chunk = -(-P // world_size)

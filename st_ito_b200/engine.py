@@ -23,8 +23,22 @@ def default_device() -> int:
     return torch.cuda.current_device()
 
 
+_CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the handle value 0 means "the library's own stream" in stito.h
+
+
 def _stream_ptr(device: int):
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """torch's current stream as a cudaStream_t.  torch's default stream is the legacy default stream (handle 0);
+    libstito reads NULL as "use my own non-blocking stream", which is not ordered against work torch has queued
+    (e.g. get_param_embeds' in-place peak normalisation of a CUDA tensor), so 0 is passed as cudaStreamLegacy."""
+    handle = int(torch.cuda.current_stream(device).cuda_stream)
+    return c_void_p(handle if handle != 0 else _CUDA_STREAM_LEGACY)
+
+
+def _wait_for_torch(t):
+    """Setup calls (set_input / set_target) run on the handle's own stream: a CUDA tensor argument may still be
+    being written by kernels queued on torch's stream."""
+    if isinstance(t, torch.Tensor) and t.is_cuda:
+        torch.cuda.current_stream(t.device).synchronize()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -126,6 +140,7 @@ class Engine:
     def __init__(self, model=None, device=None, chain: ChainDesc = None):
         self.device = default_device() if device is None else int(device)
         self.embed_dim = 512
+        self.hop, self.n_mels = 1024, 128
         self._h = c_void_p()
         self._input_key = None
         if chain is None:
@@ -140,6 +155,7 @@ class Engine:
             weights.embed_dim = model.embed_dim
             weights.bn_eps = float(model.conv_block1.bn1.eps)
             self.embed_dim = model.embed_dim
+            self.hop, self.n_mels = int(model.hop_size), int(model.mel_bins)
 
             def put(field, idx, key):
                 a = _np32(sd[key])
@@ -190,18 +206,22 @@ class Engine:
     def set_input(self, x, min_len: int = 0):
         """x: [chs, L] float32 (numpy or torch, host or device)."""
         x = self._as_f32(x)
+        _wait_for_torch(x)
         chs, L = x.shape
         check(_lib.lib().stito_set_input(self._h, ptr(x), chs, L, int(min_len)))
         return max(L, int(min_len))
 
     def set_target(self, target):
         t = self._as_f32(target)
+        _wait_for_torch(t)
         chs, L = t.shape
         check(_lib.lib().stito_set_target(self._h, ptr(t), chs, L))
 
     def set_target_embeds(self, mid, side):
         mid = self._as_f32(mid).reshape(-1)
         side = self._as_f32(side).reshape(-1)
+        _wait_for_torch(mid)
+        _wait_for_torch(side)
         check(_lib.lib().stito_set_target_embeds(self._h, ptr(mid), ptr(side), int(mid.shape[0])))
 
     def out_channels(self, chs: int) -> int:
@@ -209,33 +229,43 @@ class Engine:
 
     # -- the hot path ------------------------------------------------------------------------
     def eval_population(self, W, start: int, length: int, want_embeds: bool = False, want_audio: bool = False,
-                        in_chs: int = None):
+                        in_chs: int = None, device_out: bool = False):
         """evaluate() of style_transfer.py:474-573 for the population W [P, D] (float64).
 
-        Returns (fitness float32[P], embeds float32[2, P, E] or None, audio float32[P, chs', len] or None),
-        all as pinned host torch tensors.
+        Returns (fitness float32[P], embeds float32[2, P, E] or None, audio float32[P, chs', len] or None) as
+        pinned host torch tensors, or -- with ``device_out`` -- as tensors on this engine's GPU (what the NCCL
+        all-gather of a sharded population consumes: no host bounce).  P == 0 (an empty shard) returns empty
+        tensors.
         """
         W = np.ascontiguousarray(np.asarray(W, dtype=np.float64))
         if W.ndim != 2:
             raise ValueError("W must be [P, D]")
         P, D = W.shape
-        # pinned result buffers are cached per shape (cudaHostAlloc per generation is measurable next to a
-        # 15 ms evaluation); results are cloned out so that callers own what they get
-        fit = self._pinned("fit", (P,))
-        emb = self._pinned("emb", (2, P, self.embed_dim)) if want_embeds else None
-        aud = None
-        if want_audio:
-            ochs = self.out_channels(in_chs if in_chs is not None else 2)
-            aud = torch.empty((P, ochs, length), dtype=torch.float32, pin_memory=True)
+        ochs = self.out_channels(in_chs if in_chs is not None else 2) if want_audio else 0
+        if device_out:
+            dev = torch.device("cuda", self.device)
+            fit = torch.empty((P,), dtype=torch.float32, device=dev)
+            emb = torch.empty((2, P, self.embed_dim), dtype=torch.float32, device=dev) if want_embeds else None
+            aud = torch.empty((P, ochs, length), dtype=torch.float32, device=dev) if want_audio else None
+        else:
+            # pinned result buffers are cached per shape (cudaHostAlloc per generation is measurable next to a
+            # 15 ms evaluation); results are cloned out so that callers own what they get
+            fit = self._pinned("fit", (P,))
+            emb = self._pinned("emb", (2, P, self.embed_dim)) if want_embeds else None
+            aud = torch.empty((P, ochs, length), dtype=torch.float32, pin_memory=True) if want_audio else None
         check(_lib.lib().stito_eval_population(self._h, ptr(W), P, D, int(start), int(length), ptr(fit), ptr(emb),
                                                ptr(aud), _stream_ptr(self.device)))
+        if device_out:
+            return fit, emb, aud
         return fit.clone(), (emb.clone() if emb is not None else None), aud
 
     def _pinned(self, key, shape):
         cache = self.__dict__.setdefault("_pinned_cache", {})
         k = (key, tuple(shape))
         if k not in cache:
-            cache[k] = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+            n = int(np.prod(shape))
+            # pin_memory of a zero-element tensor is not portable across torch versions: an empty shard needs no pinning
+            cache[k] = torch.empty(shape, dtype=torch.float32, pin_memory=n > 0)
         return cache[k]
 
     def process(self, x, W, final_normalize: bool = True) -> np.ndarray:
@@ -269,8 +299,8 @@ class Engine:
     def logmel(self, x: torch.Tensor) -> torch.Tensor:
         xf = x.detach().to(torch.float32).contiguous()
         B, chs, L = xf.shape
-        T = L // 1024 + 1
-        out = torch.empty((B * chs, T, 128), dtype=torch.float32, device=xf.device)
+        T = L // self.hop + 1  # the library's own frame count (stito_logmel: T = L / hop + 1)
+        out = torch.empty((B * chs, T, self.n_mels), dtype=torch.float32, device=xf.device)
         check(_lib.lib().stito_logmel(self._h, ptr(xf), B, chs, L, ptr(out), _stream_ptr(self.device)))
         return out
 

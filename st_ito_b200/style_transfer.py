@@ -18,6 +18,7 @@ normalisation of the caller's tensors; histories appended before ``tell``.
 from __future__ import annotations
 
 import os
+import time
 from typing import List
 
 import numpy as np
@@ -200,6 +201,81 @@ def _is_fused(plugins, model, embed_func, content_model) -> bool:
             and plugins_are_native(plugins))
 
 
+class FusedEvaluator:
+    """``evaluate`` of the reference (style_transfer.py:474-573) for a chain of built-in plugins scored by the
+    AFx-Rep encoder: ONE stito_eval_population call per population (per rank).
+
+    Holds what is constant over a run -- the compiled chain, the target embeddings and the input waveform, all
+    resident on the GPU -- and applies evaluate()'s length policy, the population sharding over
+    torch.distributed ranks and the fitness all-gather.  ``run_es`` builds one; bench.py drives the same object.
+    """
+
+    crop_len = 262144
+
+    def __init__(self, engine, plugins, sample_rate, target_embed, input_audio, random_crop=False, rng=np.random,
+                 normalize_stages=False):
+        self.engine = engine
+        self.random_crop = random_crop
+        self.rng = rng
+        self.rank, self.world_size = sdist.world()
+        desc, self.D = compile_chain(plugins, sample_rate, normalize_stages)
+        engine.set_chain(desc)
+        self.target_embed = target_embed
+        engine.set_target_embeds(target_embed["mid"][0], target_embed["side"][0])
+        x = input_audio[0] if input_audio.dim() == 3 else input_audio
+        self.in_chs, self.x_len = int(x.shape[0]), int(x.shape[-1])
+        engine.set_input(x, min_len=self.crop_len)
+
+    def view_for(self, x_len: int, parallel: bool):
+        """Length policy of evaluate (reference :499-518): (start, length) into the padded input."""
+        if parallel:
+            return 0, x_len
+        if self.random_crop and (x_len - self.crop_len) > 16384:
+            # the reference draws from numpy's global RNG; a seeded run draws from its own RandomState
+            start_idx = int(self.rng.randint(16384, x_len - self.crop_len))
+            if self.world_size > 1:  # one crop for the whole population, also across ranks
+                start_idx = int(sdist.broadcast_array(np.array([float(start_idx)]))[0])
+        else:
+            start_idx = 0
+        if x_len > self.crop_len:
+            return (start_idx, self.crop_len) if self.random_crop else (0, x_len)
+        return 0, self.crop_len
+
+    def __call__(self, W, parallel=False, dropout=0.0, want_audio=False, want_embeds=False):
+        """Returns (fvals list[P], {"mid","side"} [P, E] or None, audio [P, chs', len] or None)."""
+        W = np.asarray(W, dtype=np.float64)
+        P = W.shape[0]
+        start, length = self.view_for(self.x_len, parallel)
+        want_embeds = want_embeds or dropout > 0.0
+        if self.world_size == 1:
+            fit, emb, aud = self.engine.eval_population(W, start, length, want_embeds=want_embeds,
+                                                        want_audio=want_audio, in_chs=self.in_chs)
+        else:
+            # rank r scores the slice [lo, hi) -- possibly empty when there are more ranks than candidates -- and
+            # the rows are all-gathered; on NCCL the results stay on the GPU until after the collective
+            lo, hi, _ = sdist.shard_bounds(P, self.world_size, self.rank)
+            on_gpu = sdist.backend() == "nccl"
+            fit, emb, aud = self.engine.eval_population(W[lo:hi], start, length, want_embeds=want_embeds,
+                                                        want_audio=want_audio, in_chs=self.in_chs,
+                                                        device_out=on_gpu)
+            fit = sdist.all_gather_rows(fit, P).cpu()
+            if emb is not None:
+                emb = sdist.all_gather_rows(emb.transpose(0, 1).contiguous(), P).cpu().transpose(0, 1)
+            if aud is not None:
+                aud = sdist.all_gather_rows(aud, P).cpu()
+        output_embeds = {"mid": emb[0], "side": emb[1]} if emb is not None else None
+        if dropout > 0.0:  # stochastic regulariser of the reference (:550-551), on the tiny embeddings
+            dists = []
+            for name in ("mid", "side"):
+                oe = torch.nn.functional.dropout(output_embeds[name], p=dropout)
+                dists.append(-torch.cosine_similarity(oe, self.target_embed[name].cpu().float(), dim=-1))
+            fit = torch.stack(dists, dim=0).mean(dim=0)
+            if self.world_size > 1:
+                # every rank drew its own mask; CMA-ES must see ONE fitness vector or the ranks' populations diverge
+                fit = torch.from_numpy(sdist.broadcast_array(fit.double().numpy())).float()
+        return fit.tolist(), output_embeds, aud
+
+
 def run_es(
     input_audio: torch.Tensor,
     target_audio: torch.Tensor,
@@ -226,7 +302,8 @@ def run_es(
     """Run CMA-ES optimization to find the best parameters (reference :399-692).
 
     Same arguments and result dict as the reference.  Extra keyword arguments the reference swallows
-    in **kwargs: ``seed`` (CMA-ES / find_w0 RNG) and ``verbose`` are honoured.  ``normalize_stages``
+    in **kwargs: ``seed`` (CMA-ES / find_w0 / random_crop RNG), ``verbose`` and ``iteration_times`` (a list that
+    receives the wall-clock seconds of every ask -> evaluate -> tell generation) are honoured.  ``normalize_stages``
     is swallowed exactly as in the reference, whose evaluate() and final render call process_audio
     without it (style_transfer.py:519-521, 676-678), so run_optim's --normalize-stages has no effect
     on the ES path there either.
@@ -261,23 +338,19 @@ def run_es(
     rank, world_size = sdist.world()
     crop_len = 262144
 
+    fused_eval = None
     if fused:
-        engine = model.stito_engine()
-        desc, D = compile_chain(plugins, sample_rate, normalize_stages)
-        if D != total_num_params:
-            raise ValueError(f"plugins declare {total_num_params} parameters but the chain walk consumes {D}")
-        engine.set_chain(desc)
-        engine.set_target_embeds(target_embed["mid"][0], target_embed["side"][0])
-        engine.set_input(input_audio[0], min_len=crop_len)
+        if compile_chain(plugins, sample_rate, normalize_stages)[1] != total_num_params:
+            raise ValueError(f"plugins declare {total_num_params} parameters but the chain walk consumes a different count")
+        fused_eval = FusedEvaluator(model.stito_engine(), plugins, sample_rate, target_embed, input_audio,
+                                    random_crop=random_crop, rng=rng, normalize_stages=normalize_stages)
 
     def view_for(x_len: int, parallel: bool):
-        """Length policy of evaluate (reference :499-518): (start, length) into the padded input."""
+        """Length policy of evaluate (reference :499-518) for the generic path."""
         if parallel:
             return 0, x_len
         if random_crop and (x_len - crop_len) > 16384:
-            start_idx = int(np.random.randint(16384, x_len - crop_len))
-            if world_size > 1:  # one crop for the whole population, also across ranks
-                start_idx = int(sdist.broadcast_array(np.array([float(start_idx)]))[0])
+            start_idx = int(rng.randint(16384, x_len - crop_len))
         else:
             start_idx = 0
         if x_len > crop_len:
@@ -291,28 +364,9 @@ def run_es(
         Returns (fvals list[P], output_embeds {"mid","side"} [P, E], output_audios [P, chs', L] or None).
         """
         W = np.asarray(W, dtype=np.float64)
-        P = W.shape[0]
         want_audio = savepop or content_model is not None
         if fused:
-            start, length = view_for(x.shape[-1], parallel)
-            lo, hi, _ = sdist.shard_bounds(P, world_size, rank)
-            want_embeds = dropout > 0.0 or savepop
-            fit, emb, aud = engine.eval_population(W[lo:hi], start, length, want_embeds=want_embeds,
-                                                   want_audio=want_audio, in_chs=x.shape[1])
-            if world_size > 1:
-                fit = sdist.all_gather_rows(fit, P).cpu()
-                if emb is not None:
-                    emb = sdist.all_gather_rows(emb.transpose(0, 1).contiguous(), P).cpu().transpose(0, 1)
-                if aud is not None:
-                    aud = sdist.all_gather_rows(aud, P).cpu()
-            output_embeds = {"mid": emb[0], "side": emb[1]} if emb is not None else None
-            if dropout > 0.0:  # stochastic regulariser of the reference (:550-551), on the tiny embeddings
-                dists = []
-                for name in ("mid", "side"):
-                    oe = torch.nn.functional.dropout(output_embeds[name], p=dropout)
-                    dists.append(-torch.cosine_similarity(oe, target_embeds[name].cpu().float(), dim=-1))
-                fit = torch.stack(dists, dim=0).mean(dim=0)
-            return fit.tolist(), output_embeds, aud
+            return fused_eval(W, parallel=parallel, dropout=dropout, want_audio=want_audio, want_embeds=savepop)
 
         # generic path: arbitrary plugins / embedding functions, candidate by candidate (reference loop)
         output_audios = []
@@ -384,7 +438,10 @@ def run_es(
     iters_without_improvement = 0
     x = input_audio
 
+    iteration_times = kwargs.get("iteration_times", None)  # optional list: wall seconds of every ask -> tell
+
     for iteration in range(max_iters):
+        t_iter = time.perf_counter()
         x = input_audio.clone() if not fused else input_audio  # the fused path never mutates x
         W = replicated(es.ask())
         fvals, output_embeds, output_audios = evaluate(
@@ -399,6 +456,8 @@ def run_es(
         if savepop and rank == 0:
             savepop_to_disk(iteration, fvals, output_embeds, output_audios, run_dir, sample_rate)
         es.tell(list(W), fvals)
+        if iteration_times is not None:
+            iteration_times.append(time.perf_counter() - t_iter)
         if verbose:
             es.disp()
 

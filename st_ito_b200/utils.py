@@ -106,6 +106,30 @@ def load_param_model(ckpt_path: str = None, use_gpu: bool = False):
     return model
 
 
+def centre_heads(model, clip: torch.Tensor = None):
+    """Set the head biases to ``b = -W @ mu`` where ``mu`` is the pooled feature vector of a calibration clip.
+
+    Post-ReLU pooled features share a large common-mode component, so with random weights every embedding is nearly
+    parallel to every other (cosine fitness -1 +- 1e-8: no ranking to speak of).  Cancelling the
+    calibration mean spreads the fitness over O(1) the way a trained encoder does.  Needs the B200: the raw
+    embedding of the clip with zero biases IS ``W @ mu`` (one encoder forward through libstito).
+    """
+    if clip is None:
+        g = torch.Generator().manual_seed(777)
+        t = torch.arange(40000, dtype=torch.float32) / 48000.0
+        tone = sum(torch.sin(2 * torch.pi * 110.0 * (2 ** k) * t) / (k + 1) for k in range(5))
+        clip = torch.stack([0.5 * tone + 0.1 * torch.randn(40000, generator=g),
+                            0.3 * tone + 0.1 * torch.randn(40000, generator=g)])[None]
+        clip = clip / clip.abs().max()
+    with torch.no_grad():
+        model.fc_mid.bias.zero_()
+        model.fc_side.bias.zero_()
+        mid, side = model(clip.clone())
+        model.fc_mid.bias.copy_(-mid[0].to(model.fc_mid.bias))
+        model.fc_side.bias.copy_(-side[0].to(model.fc_side.bias))
+    return model
+
+
 def make_synthetic_param_model(seed: int = 0, bn_stats: bool = True, use_gpu: bool = False, conv_gain: float = 1.0):
     """AFx-Rep architecture with seeded random weights (no checkpoint is obtainable offline).
 

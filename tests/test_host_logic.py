@@ -190,17 +190,27 @@ g = sdist.all_gather_rows(rows[lo:hi], 5)
 assert torch.equal(g, rows), g
 b = sdist.broadcast_array(np.full(4, float(rank + 1)))
 assert np.all(b == 1.0)
+# more ranks than candidates: the trailing rank owns an empty shard and still takes part in the collective
+lo1, hi1, _ = sdist.shard_bounds(1, world, rank)
+g1 = sdist.all_gather_rows(rows[:1][lo1:hi1], 1)
+assert torch.equal(g1, rows[:1]), g1
 
 class FakeEngine:  # stands in for the libstito handle: fitness = distance of w to a hidden optimum
     calls = []
     def set_chain(self, d): pass
     def set_target_embeds(self, m, s): pass
     def set_input(self, x, min_len=0): return max(x.shape[-1], min_len)
-    def eval_population(self, W, start, length, want_embeds=False, want_audio=False, in_chs=None):
+    def eval_population(self, W, start, length, want_embeds=False, want_audio=False, in_chs=None, device_out=False):
         W = np.asarray(W); FakeEngine.calls.append((W.shape[0], start, length))
-        wstar = np.linspace(0.2, 0.8, W.shape[1]) if W.shape[0] else None
+        wstar = np.linspace(0.2, 0.8, W.shape[1])
         fit = torch.tensor([float(np.sum((w - wstar) ** 2)) - 1.0 for w in W], dtype=torch.float32)
-        return fit, None, None
+        emb = None
+        if want_embeds:  # embeddings that depend on w, so that dropout changes the ranking
+            base = torch.linspace(0.0, 1.0, 512)
+            e = torch.stack([torch.cos(base * (1.0 + 7.0 * float(np.sum((w - wstar) ** 2)))) for w in W]) \
+                if W.shape[0] else torch.zeros(0, 512)
+            emb = torch.stack([e, e])
+        return fit, emb, None
 
 model = make_synthetic_param_model(seed=1)
 model.stito_engine = lambda *a, **k: FakeEngine()
@@ -211,8 +221,8 @@ with contextlib.redirect_stdout(io.StringIO()):
     plugins, D, _ = style_transfer.load_plugins(effects.make_chain("eq"))
 x = torch.randn(1, 1, 300000, generator=torch.Generator().manual_seed(0))
 t = torch.randn(1, 1, 300000, generator=torch.Generator().manual_seed(1))
-res = style_transfer.run_es(x, t, 48000, plugins, model, get_param_embeds, max_iters=6, popsize=10, sigma0=0.33,
-                            find_w0=True, seed={seed}, verbose=False)
+res = style_transfer.run_es(x, t, 48000, plugins, model, get_param_embeds, max_iters=6, popsize={popsize}, sigma0=0.33,
+                            find_w0=True, seed={seed}, verbose=False, dropout={dropout}, random_crop={random_crop})
 json.dump({{"fopt": res["fopt"], "wopt": list(map(float, res["wopt"])), "hist": [float(v) for v in res["fval_history"][1:]],
            "calls": FakeEngine.calls}}, open(out, "w"))
 if world > 1:
@@ -220,9 +230,9 @@ if world > 1:
 '''
 
 
-def _run_world(world, seed, tmp_path, port):
+def _run_world(world, seed, tmp_path, port, popsize=10, dropout=0.0, random_crop=False):
     script = tmp_path / f"worker_{world}_{seed}.py"
-    script.write_text(_WORKER.format(root=ROOT, seed=seed))
+    script.write_text(_WORKER.format(root=ROOT, seed=seed, popsize=popsize, dropout=dropout, random_crop=random_crop))
     outs = [tmp_path / f"out_{world}_{seed}_{r}.json" for r in range(world)]
     procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world), str(port), str(outs[r])],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
@@ -249,6 +259,18 @@ def test_run_es_population_sharding_world2_gloo(tmp_path, seed):
         assert one["fopt"] == two[0]["fopt"] and one["wopt"] == two[0]["wopt"]
         assert all(c == [10, 0, 300000] for c in one["calls"])
         assert one["fopt"] <= min(one["hist"]) and one["fopt"] < 0.5  # best-so-far of a distance-to-optimum objective
+
+
+def test_run_es_sharding_uneven_population_dropout_and_crop_world2_gloo(tmp_path):
+    """(a) a population that does not divide over the ranks (7 = 4 + 3); (b) dropout > 0 draws a different
+    mask on every rank, so the fitness vector CMA-ES sees is rank 0's, broadcast; (c) the random crop is one draw for
+    the whole population on every rank.  The two ranks must stay in lock step: identical trajectories."""
+    port = 29950 + (os.getpid() % 40)
+    two = _run_world(2, "3", tmp_path, port, popsize=7, dropout=0.3, random_crop=True)
+    assert two[0]["wopt"] == two[1]["wopt"] and two[0]["hist"] == two[1]["hist"] and two[0]["fopt"] == two[1]["fopt"]
+    assert [c[0] for c in two[0]["calls"]] == [4] * 7 and [c[0] for c in two[1]["calls"]] == [3] * 7
+    starts0, starts1 = [c[1] for c in two[0]["calls"]], [c[1] for c in two[1]["calls"]]
+    assert starts0 == starts1 and len(set(starts0)) > 1 and all(c[2] == 262144 for c in two[0]["calls"])
 
 
 # ------------------------------------------------------------------------- checkpoint loading (CPU only)
