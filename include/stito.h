@@ -104,8 +104,9 @@ typedef struct {
     /* -- appended in ABI 2.0.0 -- */
     int32_t comp_fallbacks;      /* compressor super-blocks whose time-parallel Newton iteration did not converge
                                     and were recomputed by the exact serial loop (results stay correct)          */
-    int32_t act_overflow;        /* 1: an activation left the fp16x3 range; the call was redone with precision 0
-                                    and the handle stays at precision 0                                          */
+    int32_t act_overflow;        /* times the call was redone because the per-layer storage scales of the fp16x3
+                                    encoder were (re-)calibrated: 1 on a handle's first encoder pass, > 0 later only
+                                    when an activation left the fp16 range (results are those of the last pass)  */
 } stito_timing;
 
 /* Create an evaluator for (chain, encoder) on CUDA device `device`.  `weights` may be NULL:
@@ -119,7 +120,9 @@ STITO_API void stito_destroy(stito_handle *h);
 STITO_API int stito_set_chain(stito_handle *h, const stito_chain_desc *chain);
 
 /* Encoder arithmetic: 0 = fp32 CUDA cores (bit-for-bit conv semantics of the oracle up to
- * summation order), 1 = error-compensated fp16x3 on tcgen05 tensor cores (default). */
+ * summation order), 1 = error-compensated fp16x3 on tcgen05 tensor cores (default).  Mode 1 stores activations as
+ * fp16 hi/lo pairs of value * 2^shift with a per-layer shift that the library calibrates from the measured
+ * per-layer maxima on the handle's first encoder pass and widens whenever a later input would overflow. */
 STITO_API int stito_set_precision(stito_handle *h, int precision);
 
 /* Upload the input waveform x[chs, L].  The device copy is zero-padded to max(L, min_len) so

@@ -151,13 +151,22 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr float kActScale = 64.0f;  // activations are stored as fp16 hi/lo of (value * 2^6)
+// Activations are stored as fp16 hi/lo pairs of (value * 2^shift): the shift is per layer (TcWorkspace::act_shift,
+// default 6) and calibrated from the measured per-layer maxima so that the pairs neither overflow (65504) nor lose
+// their lo parts to the subnormal range, whatever the scale of a checkpoint's BatchNorm statistics.
 constexpr float kHalfMax = 65504.0f;
+
+__device__ __forceinline__ void publish_amax(unsigned *amax, float mx) {
+    // warp maximum of the (non-negative, already scaled) outputs -> one atomic per warp; float bits order like unsigned
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (amax != nullptr && (threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(amax, __float_as_uint(mx));
+}
 
 struct ConvTcParams {
     const float *bias;   // [Cout]
-    float unscale;       // 2^-shift of the weight pre-scaling / kActScale of the input
-    float out_scale;     // kActScale for fp16-pair outputs
+    float unscale;       // 2^-shift of the weight pre-scaling / 2^shift of the input activations
+    float out_scale;     // 2^shift of this layer's output pairs (x 0.25 with the fused average pool); 1 for fp32 output
     __half *out_hi, *out_lo;  // NHWC fp16 pair, or
     float *out_f32;           // NHWC fp32 (when non-null)
     int N, H, W, Cin, Cout;
@@ -172,9 +181,11 @@ struct ConvTcParams {
     // Compensation of the tensor core's truncating fp32 accumulate: every drained chunk partial sum is multiplied by
     // 1 + trunc_comp * (number of K = 16 MMA steps accumulated into it); see chunk_comp().
     float trunc_comp;
-    // fp16 range guard: activations are stored as fp16 pairs of (value * 2^6); anything above kHalfMax is clamped and
-    // *overflow (device int, nullable) is raised so that the caller can redo the evaluation with the fp32 encoder.
+    // fp16 range guard: anything above kHalfMax is clamped and *overflow (device int, nullable) is raised; *amax (device,
+    // nullable) receives the largest stored (scaled) value of the layer as float bits.  The caller re-calibrates the
+    // per-layer shifts from amax and redoes the evaluation after an overflow.
     int *overflow;
+    unsigned *amax;
 };
 
 constexpr int kTileM = 128;
@@ -211,6 +222,7 @@ __device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&
         store = img < p.IPT && (n0 + img) < p.N && hh < p.H && ww < p.W;
         obase = (((int64_t)(n0 + img) * p.H + hh) * p.W + ww) * p.Cout + cbase;
     }
+    float mx = 0.0f;
 #pragma unroll
     for (int j0 = 0; j0 < kCols; j0 += 8) {
         float y[8];
@@ -236,6 +248,7 @@ __device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&
             bool ovf = false;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {  // post-ReLU: only the upper bound can be hit (NaN compares false and passes through)
+                mx = fmaxf(mx, y[j]);
                 ovf |= y[j] > kHalfMax;
                 y[j] = fminf(y[j], kHalfMax);
             }
@@ -252,6 +265,7 @@ __device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&
             *reinterpret_cast<uint4 *>(p.out_lo + obase + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
+    if (p.out_f32 == nullptr) publish_amax(p.amax, mx);  // every lane of the warp gets here (uniform call sites)
 }
 
 // Persistent, warp-specialised implicit-GEMM convolution.
@@ -677,7 +691,9 @@ __global__ void __launch_bounds__(256) wino_out_kernel(const float *__restrict__
                                                        float unscale, __half *__restrict__ out_hi,
                                                        __half *__restrict__ out_lo, float *__restrict__ out_f32, int N,
                                                        int H, int W, int Cout, int th, int tw, int Tp, int pool,
-                                                       int *__restrict__ overflow) {
+                                                       float out_scale, int *__restrict__ overflow,
+                                                       unsigned *__restrict__ amax) {
+    float mx = 0.0f;
     const int C2 = Cout >> 1;
     const int64_t total = (int64_t)N * th * tw * C2;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -713,7 +729,8 @@ __global__ void __launch_bounds__(256) wino_out_kernel(const float *__restrict__
             float o[2];
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
-                o[ch] = ((y[0][0][ch] + y[0][1][ch]) + (y[1][0][ch] + y[1][1][ch])) * (0.25f * kActScale);
+                o[ch] = ((y[0][0][ch] + y[0][1][ch]) + (y[1][0][ch] + y[1][1][ch])) * (0.25f * out_scale);
+                mx = fmaxf(mx, o[ch]);
                 if (o[ch] > kHalfMax) { o[ch] = kHalfMax; if (overflow != nullptr) atomicOr(overflow, 1); }
             }
             const size_t oo = (((size_t)n * Ho + ty) * Wo + tx) * Cout + 2 * c2;
@@ -732,7 +749,8 @@ __global__ void __launch_bounds__(256) wino_out_kernel(const float *__restrict__
                     if (out_f32 != nullptr) {
                         *reinterpret_cast<float2 *>(out_f32 + oo) = make_float2(y[i][j][0], y[i][j][1]);
                     } else {
-                        float a = y[i][j][0] * kActScale, b = y[i][j][1] * kActScale;
+                        float a = y[i][j][0] * out_scale, b = y[i][j][1] * out_scale;
+                        mx = fmaxf(mx, fmaxf(a, b));
                         if (a > kHalfMax || b > kHalfMax) {
                             a = fminf(a, kHalfMax); b = fminf(b, kHalfMax);
                             if (overflow != nullptr) atomicOr(overflow, 1);
@@ -745,6 +763,7 @@ __global__ void __launch_bounds__(256) wino_out_kernel(const float *__restrict__
                 }
         }
     }
+    publish_amax(amax, mx);
 }
 
 // ------------------------------------------------------------ SIMT helpers of the fp16x3 path
@@ -756,7 +775,9 @@ constexpr int kC1Px = 4;
 __global__ void __launch_bounds__(256) tc_conv_first_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                             const float *__restrict__ bias, __half *__restrict__ yh,
                                                             __half *__restrict__ yl, int N, int H, int W,
-                                                            int *__restrict__ overflow) {
+                                                            float out_scale, int *__restrict__ overflow,
+                                                            unsigned *__restrict__ amax) {
+    float mx = 0.0f;
     const int g = threadIdx.x & 7;
     float wr[9][8], br[8];
 #pragma unroll
@@ -800,8 +821,9 @@ __global__ void __launch_bounds__(256) tc_conv_first_kernel(const float *__restr
                         a0 = fmaf(v[kh][px + kw], wr[kh * 3 + kw][2 * c2], a0);
                         a1 = fmaf(v[kh][px + kw], wr[kh * 3 + kw][2 * c2 + 1], a1);
                     }
-                a0 = fmaxf(a0 + br[2 * c2], 0.f) * kActScale;
-                a1 = fmaxf(a1 + br[2 * c2 + 1], 0.f) * kActScale;
+                a0 = fmaxf(a0 + br[2 * c2], 0.f) * out_scale;
+                a1 = fmaxf(a1 + br[2 * c2 + 1], 0.f) * out_scale;
+                mx = fmaxf(mx, fmaxf(a0, a1));
                 if (a0 > kHalfMax || a1 > kHalfMax) {
                     a0 = fminf(a0, kHalfMax); a1 = fminf(a1, kHalfMax);
                     if (overflow != nullptr) atomicOr(overflow, 1);
@@ -816,6 +838,7 @@ __global__ void __launch_bounds__(256) tc_conv_first_kernel(const float *__restr
             *reinterpret_cast<uint4 *>(yl + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
+    publish_amax(amax, mx);
 }
 
 // ---------------------------------------------------------------------- host side
@@ -1141,11 +1164,13 @@ void tc_workspace_release(TcWorkspace *ws) {
 }
 
 // One conv layer on tensor cores: in (hi, lo) NHWC [N][H][W][Cin] -> out fp16 pair or fp32.
-static int conv_tc(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, const __half *in_hi, const __half *in_lo,
+static int conv_tc(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, int li, const __half *in_hi, const __half *in_lo,
                    __half *out_hi, __half *out_lo, float *out_f32, int N, int H, int W, bool pool, int *launches) {
+    const float in_scale = std::ldexp(1.0f, ws.act_shift[li - 1]), out_scale = std::ldexp(1.0f, ws.act_shift[li]);
     ConvTcParams p{};
-    p.bias = l.bias; p.unscale = l.w_unscale / kActScale;
-    p.out_scale = out_f32 ? 1.0f : (pool ? 0.25f * kActScale : kActScale);  // exact powers of two
+    p.bias = l.bias; p.unscale = l.w_unscale / in_scale;
+    p.out_scale = out_f32 ? 1.0f : (pool ? 0.25f * out_scale : out_scale);  // exact powers of two
+    p.amax = ws.amax ? ws.amax + li : nullptr;
     p.pool = pool ? 1 : 0;
     p.trunc_comp = chunk_comp();
     p.overflow = ws.overflow_flag;
@@ -1213,8 +1238,9 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, const _
 
 // One deep conv layer through Winograd F(2x2,3x3): input transform -> 16 GEMMs (conv3x3_tc_kernel, GEMM mode) ->
 // output transform (+ bias, ReLU, optional 2x2 pool, hi/lo split or fp32).
-static int conv_wino(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, const __half *in_hi, const __half *in_lo,
+static int conv_wino(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, int li, const __half *in_hi, const __half *in_lo,
                      __half *out_hi, __half *out_lo, float *out_f32, int N, int H, int W, bool pool, int *launches) {
+    const float in_scale = std::ldexp(1.0f, ws.act_shift[li - 1]), out_scale = std::ldexp(1.0f, ws.act_shift[li]);
     const int th = (H + 1) / 2, tw = (W + 1) / 2;
     const int T = N * th * tw;
     const int Tp = (T + kTileM - 1) / kTileM * kTileM;
@@ -1242,9 +1268,10 @@ static int conv_wino(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, const
     if (!(bl = make_w_map(ws, l.u_lo, 16 * l.cout, l.cin, 256, slabk))) return -1;
     int rc = slabk == 32 ? launch_conv_tc_t<256, 4, 32>(st, *ah, *al, *bh_, *bl, p) : launch_conv_tc_t<256, 2, 64>(st, *ah, *al, *bh_, *bl, p);
     if (rc) return rc;
-    const float unscale = l.u_unscale / (kActScale * kWinoVScale);
+    const float unscale = l.u_unscale / (in_scale * kWinoVScale);
     wino_out_kernel<<<blocks_for((int64_t)T * (l.cout / 2), 256), 256, 0, st>>>(M, l.bias, unscale, out_hi, out_lo, out_f32, N, H, W,
-                                                                                  l.cout, th, tw, Tp, pool ? 1 : 0, ws.overflow_flag);
+                                                                                  l.cout, th, tw, Tp, pool ? 1 : 0, out_scale, ws.overflow_flag,
+                                                                                  ws.amax ? ws.amax + li : nullptr);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tc_fail("winograd transform launch", cudaGetErrorString(e));
     *launches += 3;
@@ -1269,25 +1296,26 @@ int tc_encoder_forward(cudaStream_t st, const EncoderDev &enc, TcWorkspace &ws, 
         if (ev) cudaEventRecord(ev[2 * b], st);
         if (b == 0) {
             if ((uint64_t)px >= (1ull << 31)) return tc_fail("tc_encoder_forward", "micro-batch too large for 32-bit pixel indices");
-            tc_conv_first_kernel<<<blocks_for((int64_t)px * 8 / kC1Px, 256), 256, 0, st>>>(feat, l1.w, l1.bias, m_hi, m_lo, N, H, W, ws.overflow_flag);
+            tc_conv_first_kernel<<<blocks_for((int64_t)px * 8 / kC1Px, 256), 256, 0, st>>>(feat, l1.w, l1.bias, m_hi, m_lo, N, H, W, std::ldexp(1.0f, ws.act_shift[0]),
+                                                                                           ws.overflow_flag, ws.amax);
             *launches += 1;
         } else {
             if (wino_layer(l1) && use_wino()) {
-                if (conv_wino(st, l1, ws, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
-            } else if (conv_tc(st, l1, ws, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
+                if (conv_wino(st, l1, ws, 2 * b, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
+            } else if (conv_tc(st, l1, ws, 2 * b, in_hi, in_lo, m_hi, m_lo, nullptr, N, H, W, false, launches)) return -1;
         }
         if (ev) cudaEventRecord(ev[2 * b + 1], st);
         const bool wino2 = wino_layer(l2) && use_wino();
         if (b < 5) {  // conv2 + ReLU + 2x2 average pool + hi/lo split in one kernel -> next block's input
             if (wino2) {
-                if (conv_wino(st, l2, ws, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
-            } else if (conv_tc(st, l2, ws, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
+                if (conv_wino(st, l2, ws, 2 * b + 1, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
+            } else if (conv_tc(st, l2, ws, 2 * b + 1, m_hi, m_lo, in_hi, in_lo, nullptr, N, H, W, true, launches)) return -1;
             H /= 2;
             W /= 2;
         } else {
             if (wino2) {
-                if (conv_wino(st, l2, ws, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, false, launches)) return -1;
-            } else if (conv_tc(st, l2, ws, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, false, launches)) return -1;
+                if (conv_wino(st, l2, ws, 2 * b + 1, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, false, launches)) return -1;
+            } else if (conv_tc(st, l2, ws, 2 * b + 1, m_hi, m_lo, nullptr, nullptr, c2, N, H, W, false, launches)) return -1;
         }
     }
     if (ev) cudaEventRecord(ev[12], st);

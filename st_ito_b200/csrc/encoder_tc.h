@@ -33,6 +33,11 @@ struct TcWorkspace {
     size_t cap[kBufs] = {};
     std::vector<TcMapEntry *> maps;  // descriptor cache (cleared whenever a buffer is reallocated)
     int *overflow_flag = nullptr;    // device int: set when an activation exceeded the fp16 range (see store_tile)
+    // Per-layer storage scale of the fp16 hi/lo activation pairs: layer l's output is stored as value * 2^act_shift[l]
+    // (layer 11 writes fp32).  Calibrated by the C-ABI layer from `amax` (device, 12 unsigned = float bits of the largest
+    // stored value per layer, nullable).
+    int act_shift[12] = {6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6};
+    unsigned *amax = nullptr;
 };
 
 // true when the tcgen05 encoder is compiled in and enabled

@@ -145,6 +145,7 @@ void biquad_design(double gain_db, double fc, double q, double fs, int type, dou
 }
 
 constexpr int kNumEvents = 8;
+constexpr int kNumFlags = 16;  // see stito_handle::flags
 
 }  // namespace
 
@@ -175,7 +176,9 @@ struct stito_handle {
     HostBuf hparams, hW, hflags;
     // flags (device ints): [0], [1] NaN in mid / side embeddings; [2] an activation left the fp16 range of the fp16x3
     // encoder; [3] compressor super-blocks redone serially (Newton iteration did not converge)
-    bool warned_overflow = false;
+    //        [4..15] per conv layer: float bits of the largest stored activation (tensor-core path)
+    bool tc_calibrated = false;  // per-layer activation scales (tcws.act_shift) have been measured on this handle
+    int tc_attempts = 0;
     int comp_fallbacks_total = 0;
     ReverbGeom rgeom{};
     TcWorkspace tcws;
@@ -186,6 +189,42 @@ struct stito_handle {
     stito_timing timing{};
     bool timing_pending = false;
 };
+
+// After a synchronised pass of the tensor-core encoder: calibrate the per-layer storage scales of the fp16 hi/lo
+// activation pairs from the measured per-layer maxima (hflags[4..15], float bits of the largest STORED value).
+//   * first pass on this handle: shift_l = floor(log2(16384 / max_l)) -- a factor 4 of head-room below the fp16 maximum,
+//     lo parts far above the subnormal range; if any shift changed the pass is redone once with the new scales;
+//   * later: only an overflow (hflags[2]: a stored value exceeded 65504 and was clamped) re-calibrates -- maxima only ever
+//     widen the range -- and the pass is redone; layers downstream of a clamped one are re-measured by that pass.
+// Returns true when the caller must redo the pass.  After 14 fruitless attempts the handle drops to the fp32 encoder.
+static bool tc_after_pass(stito_handle *h) {
+    if (h->precision != 1) return false;
+    const int *hf = h->hflags.as<int>();
+    const bool overflow = hf[2] != 0;
+    if (h->tc_calibrated && !overflow) { h->tc_attempts = 0; return false; }
+    if (++h->tc_attempts > 14) {
+        fprintf(stderr, "libstito: could not find fp16x3 activation scales without overflow; this handle now uses the fp32 "
+                        "CUDA-core encoder\n");
+        h->precision = 0;
+        h->tc_attempts = 0;
+        return true;
+    }
+    bool changed = false;
+    for (int l = 0; l < 11; ++l) {  // layer 11 (block 6 conv 2) writes fp32
+        float stored;
+        memcpy(&stored, &hf[4 + l], sizeof(float));
+        if (!(stored > 0.0f) || !std::isfinite(stored)) continue;
+        const double true_max = (double)stored / std::ldexp(1.0, h->tcws.act_shift[l]);
+        int ns = (int)std::floor(std::log2(16384.0 / true_max));
+        if (ns > 24) ns = 24;
+        if (ns < -12) ns = -12;
+        if (h->tc_calibrated && ns > h->tcws.act_shift[l]) ns = h->tcws.act_shift[l];  // after calibration: only widen
+        if (ns != h->tcws.act_shift[l]) { h->tcws.act_shift[l] = ns; changed = true; }
+    }
+    h->tc_calibrated = !overflow;
+    if (!changed && !overflow) { h->tc_attempts = 0; return false; }
+    return true;
+}
 
 namespace {
 
@@ -478,10 +517,11 @@ int stito_create(const stito_chain_desc *chain, const stito_encoder_weights *wts
     CUB(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     for (int i = 0; i < kNumEvents; ++i) CUB(cudaEventCreate(&h->ev[i]));
     for (int i = 0; i < 13; ++i) CUB(cudaEventCreate(&h->ev_conv[i]));
-    CUB(h->flags.ensure(4 * sizeof(int)));
-    CUB(cudaMemset(h->flags.p, 0, 4 * sizeof(int)));
-    CUB(h->hflags.ensure(4 * sizeof(int)));
+    CUB(h->flags.ensure(kNumFlags * sizeof(int)));
+    CUB(cudaMemset(h->flags.p, 0, kNumFlags * sizeof(int)));
+    CUB(h->hflags.ensure(kNumFlags * sizeof(int)));
     h->tcws.overflow_flag = h->flags.as<int>() + 2;
+    h->tcws.amax = h->flags.as<unsigned>() + 4;
 
     if (wts) {
         if (wts->n_fft != 2048 || wts->hop <= 0 || wts->n_mels != 128 || wts->embed_dim <= 0 ||
@@ -641,8 +681,14 @@ int stito_set_target(stito_handle *h, const float *target, int chs, int64_t L) {
     CU(launch_peak(st, v, 1, chs, L, h->peaks.as<unsigned>(), &launches));
     CU(h->target.ensure((size_t)2 * E * sizeof(float)));
     float *mid = h->target.as<float>(), *side = mid + E;
-    int rc = encoder_forward(h, st, v, h->peaks.as<unsigned>(), 1, chs, L, mid, side, &launches, false);
-    if (rc) return rc;
+    for (;;) {
+        CU(cudaMemsetAsync(h->flags.as<int>() + 2, 0, (kNumFlags - 2) * sizeof(int), st));
+        int rc = encoder_forward(h, st, v, h->peaks.as<unsigned>(), 1, chs, L, mid, side, &launches, false);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(h->hflags.p, h->flags.p, kNumFlags * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (!tc_after_pass(h)) break;
+    }
     CU(launch_embed_normalize(st, mid, side, 1, E, h->flags.as<int>(), &launches));
     CU(cudaStreamSynchronize(st));
     h->has_target = true;
@@ -678,7 +724,7 @@ static int enqueue_population(stito_handle *h, cudaStream_t st, const double *Wh
     float *mid_all = h->emb.as<float>(), *side_all = mid_all + (size_t)P * E;
     int launches = 0;
     SigView in{h->input.as<float>() + start, 0, h->in_cap};
-    CU(cudaMemsetAsync(h->flags.as<int>() + 2, 0, 2 * sizeof(int), st));
+    CU(cudaMemsetAsync(h->flags.as<int>() + 2, 0, (kNumFlags - 2) * sizeof(int), st));
     CU(cudaEventRecord(h->ev[0], st));
     for (int p0 = 0; p0 < P; p0 += h->microbatch) {
         const int pb = (P - p0) < h->microbatch ? (P - p0) : h->microbatch;
@@ -712,7 +758,7 @@ static int enqueue_population(stito_handle *h, cudaStream_t st, const double *Wh
     CU(cudaEventRecord(h->ev[6], st));
     if (fitness) CU(cudaMemcpyAsync(fitness, h->fit.p, (size_t)P * sizeof(float), cudaMemcpyDefault, st));
     if (embeds) CU(cudaMemcpyAsync(embeds, h->emb.p, (size_t)2 * P * E * sizeof(float), cudaMemcpyDefault, st));
-    CU(cudaMemcpyAsync(h->hflags.p, h->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->hflags.p, h->flags.p, kNumFlags * sizeof(int), cudaMemcpyDeviceToHost, st));
     *launches_out += launches;
     return STITO_OK;
 }
@@ -739,27 +785,17 @@ int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_
     const int chs = h->in_chs;
     const int ochs = out_channels(h->chain, chs);
     int launches = 0;
-    rc = enqueue_population(h, st, Wh, P, D, start, len, fitness, embeds, audio, &launches);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(st));
-    const int *hf = h->hflags.as<int>();
-    int comp_fallbacks = hf[3];
-    int overflowed = 0;
-    if (hf[2] != 0 && h->precision == 1) {
-        // An activation exceeded what the fp16 hi/lo pairs of the tensor-core path can hold (|value| > 1023.5 after a
-        // ReLU): the result above is clamped, i.e. wrong.  Redo the evaluation with the fp32 CUDA-core encoder and keep
-        // the handle there (a checkpoint with such BatchNorm scales would trip on every generation).
-        if (!h->warned_overflow) {
-            fprintf(stderr, "libstito: activations exceed the fp16x3 range of the tensor-core encoder; this handle now uses "
-                            "the fp32 CUDA-core encoder (stito_set_precision(h, 1) to switch back)\n");
-            h->warned_overflow = true;
-        }
-        h->precision = 0;
-        overflowed = 1;
+    // An activation that exceeds what the fp16 hi/lo pairs of the tensor-core path can hold is clamped, i.e. the result is
+    // wrong: tc_after_pass() re-calibrates the per-layer scales (or, as a last resort, drops to the fp32 encoder) and the
+    // evaluation is redone.  Steady state: one pass.
+    int overflowed = 0, comp_fallbacks = 0;
+    for (;;) {
         rc = enqueue_population(h, st, Wh, P, D, start, len, fitness, embeds, audio, &launches);
         if (rc) return rc;
         CU(cudaStreamSynchronize(st));
-        comp_fallbacks = hf[3];
+        comp_fallbacks = h->hflags.as<int>()[3];
+        if (!tc_after_pass(h)) break;
+        ++overflowed;
     }
     h->comp_fallbacks_total += comp_fallbacks;
     // timing of this call
@@ -806,6 +842,7 @@ int stito_process(stito_handle *h, const float *x, int chs, int64_t L, const dou
     const int ochs = out_channels(h->chain, chs);
     const bool ydev = is_device_ptr(y);
     int launches = 0;
+    CU(cudaMemsetAsync(h->flags.as<int>() + 2, 0, (kNumFlags - 2) * sizeof(int), st));
     for (int p0 = 0; p0 < P; p0 += h->microbatch) {
         const int pb = (P - p0) < h->microbatch ? (P - p0) : h->microbatch;
         const float *res = nullptr;
@@ -830,7 +867,13 @@ int stito_process(stito_handle *h, const float *x, int chs, int64_t L, const dou
         }
         CU(cudaStreamSynchronize(st));
     }
+    CU(cudaMemcpyAsync(h->hflags.p, h->flags.p, kNumFlags * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memset(&h->timing, 0, sizeof(h->timing));
     h->timing.launches = launches;
+    h->timing.precision = h->precision;
+    h->timing.comp_fallbacks = h->hflags.as<int>()[3];
+    h->comp_fallbacks_total += h->timing.comp_fallbacks;
     return STITO_OK;
 }
 
@@ -857,17 +900,27 @@ int stito_embed(stito_handle *h, const float *x, int B, int chs, int64_t L, int 
         CU(cudaMemsetAsync(h->peaks.p, 0, (size_t)B * sizeof(unsigned), st));
         CU(launch_peak(st, all, B, chs, L, h->peaks.as<unsigned>(), &launches));
     }
-    for (int b0 = 0; b0 < B; b0 += h->microbatch) {
-        const int bb = (B - b0) < h->microbatch ? (B - b0) : h->microbatch;
-        SigView v{xd + (size_t)b0 * chs * L, (int64_t)chs * L, L};
-        int rc = encoder_forward(h, st, v, peak_normalize ? h->peaks.as<unsigned>() + b0 : nullptr, bb, chs, L,
-                                 mid_d + (size_t)b0 * E, side_d + (size_t)b0 * E, &launches, false);
-        if (rc) return rc;
+    int overflowed = 0;
+    for (;;) {
+        CU(cudaMemsetAsync(h->flags.as<int>() + 2, 0, (kNumFlags - 2) * sizeof(int), st));
+        for (int b0 = 0; b0 < B; b0 += h->microbatch) {
+            const int bb = (B - b0) < h->microbatch ? (B - b0) : h->microbatch;
+            SigView v{xd + (size_t)b0 * chs * L, (int64_t)chs * L, L};
+            int rc = encoder_forward(h, st, v, peak_normalize ? h->peaks.as<unsigned>() + b0 : nullptr, bb, chs, L,
+                                     mid_d + (size_t)b0 * E, side_d + (size_t)b0 * E, &launches, false);
+            if (rc) return rc;
+        }
+        CU(cudaMemcpyAsync(mid, mid_d, (size_t)B * E * sizeof(float), cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(side, side_d, (size_t)B * E * sizeof(float), cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(h->hflags.p, h->flags.p, kNumFlags * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (!tc_after_pass(h)) break;  // else: activation scales re-calibrated -> once more
+        ++overflowed;
     }
-    CU(cudaMemcpyAsync(mid, mid_d, (size_t)B * E * sizeof(float), cudaMemcpyDefault, st));
-    CU(cudaMemcpyAsync(side, side_d, (size_t)B * E * sizeof(float), cudaMemcpyDefault, st));
-    CU(cudaStreamSynchronize(st));
+    memset(&h->timing, 0, sizeof(h->timing));
     h->timing.launches = launches;
+    h->timing.precision = h->precision;
+    h->timing.act_overflow = overflowed;
     return STITO_OK;
 }
 

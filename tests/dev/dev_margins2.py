@@ -1,0 +1,75 @@
+"""Developer probe (GPU), also run by tests/test_gpu_parity.py::test_encoder_gate_on_a_second_weight_distribution in a
+subprocess (the knobs are read from the environment once per process): embedding error of the tensor-core encoder on a
+SECOND weight distribution -- heavy-tailed (log-normal magnitude) convolution weights, BatchNorm scales that are
+nearly zero on some channels and large on others, shifted running means -- for the current STITO_TC_COMP /
+STITO_TC_CHUNK.  VERDICT r1 item 8b: the accumulate compensation was fitted on ONE Xavier-uniform fixture.
+Prints one JSON line: {"fixture": ..., "err": {"short": [mid, side], "long": [mid, side]}, "fit_err": ...}."""
+import json, math, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import cnn14
+from st_ito_b200.utils import get_param_embeds, make_synthetic_param_model
+from tests.signals import test_signal
+
+SR = 48000
+
+
+def heavy_tail_(model, seed=99):
+    """Same perturbation, from the same seeded generator, for the oracle model and the CUDA-path model."""
+    g = torch.Generator().manual_seed(seed)
+    for name, mod in model.named_modules():
+        if isinstance(mod, torch.nn.Conv2d):
+            w = mod.weight.data
+            w2 = w * torch.exp(0.75 * torch.randn(w.shape, generator=g))   # log-normal magnitudes: kurtosis ~ 25
+            mod.weight.data = w2 * (w.std() / w2.std())
+        elif isinstance(mod, torch.nn.BatchNorm2d) and name != "bn0":
+            n = mod.num_features
+            u = torch.rand(n, generator=g)
+            gamma = torch.where(u < 0.15, 0.02 + 0.03 * torch.rand(n, generator=g),
+                                torch.where(u > 0.85, 2.5 + 1.5 * torch.rand(n, generator=g),
+                                            0.6 + 0.8 * torch.rand(n, generator=g)))
+            mod.weight.data = gamma / gamma.pow(2).mean().sqrt() * 1.4   # RMS gain ~ the first fixture's: activations stay O(1)
+            mod.bias.data = 0.3 * torch.randn(n, generator=g)
+            mod.running_mean.data = 0.3 * torch.randn(n, generator=g)
+            mod.running_var.data = torch.exp(torch.empty(n).uniform_(math.log(0.2), math.log(4.0), generator=g))
+
+
+def main():
+    fixture = sys.argv[1] if len(sys.argv) > 1 else "heavy"
+    ours = make_synthetic_param_model(seed=3, bn_stats=True, conv_gain=2.0)
+    ref = cnn14.make_encoder(seed=3, bn_stats=True, conv_gain=2.0)
+    if fixture == "heavy":
+        heavy_tail_(ours)
+        heavy_tail_(ref)
+    for k in ("conv_block4.conv1.weight", "conv_block6.bn2.weight", "conv_block1.bn1.running_var"):
+        assert torch.equal(ours.state_dict()[k], ref.state_dict()[k]), k
+    cnn14.centre_heads(ref)
+    with torch.no_grad():
+        ours.fc_mid.bias.copy_(ref.fc_mid.bias)
+        ours.fc_side.bias.copy_(ref.fc_side.bias)
+    ours.stito_engine().set_precision(int(os.environ.get("DEV_PRECISION", "1")))
+    out = {"fixture": fixture, "comp": os.environ.get("STITO_TC_COMP", "default"),
+           "chunk": os.environ.get("STITO_TC_CHUNK", "default"), "err": {}}
+    for tag, L, B in (("short", 40000, 6), ("long", 480000, 2)):
+        x = torch.from_numpy(np.stack([test_signal(2, L, seed=500 + b) for b in range(B)]))
+        want = cnn14.get_param_embeds(x.clone(), ref, SR)
+        got = get_param_embeds(x.clone(), ours, SR)
+        e = []
+        for k in ("mid", "side"):
+            a, b = got[k].numpy().astype(np.float64), want[k].numpy().astype(np.float64)
+            e.append(float((np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)).max()))
+        out["err"][tag] = e
+        if tag == "short":
+            te = {k: v[:1] for k, v in want.items()}
+            fa = cnn14.fitness(got, te).numpy()[1:]
+            fb = cnn14.fitness(want, te).numpy()[1:]
+            out["fit_err"] = float(np.max(np.abs(fa - fb) / np.maximum(np.abs(fb), 1e-3)))
+            out["fit_spread"] = [float(fb.min()), float(fb.max())]
+    t = ours.stito_engine().timing()
+    out["precision"], out["act_overflow"] = t["precision"], t["act_overflow"]
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

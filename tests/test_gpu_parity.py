@@ -583,3 +583,320 @@ def test_config4_shape_30s_stereo(models_centred, oracle_dsp):
     err = np.abs(aud[0].numpy() - ref0)
     assert err.max() <= 3e-5 and err.mean() <= 5e-6, (err.max(), err.mean())
     np.testing.assert_array_equal(aud[1].numpy(), tgt)
+
+
+# ------------------------------------------------------------------ BASELINE configs at full size vs the oracle
+def oracle_population(oracle_dsp, x, W, oplugins, ref, te, pad=True):
+    """oracle.cnn14.evaluate for a whole population, candidates rendered on a pool of host threads (the C kernels
+    release the GIL; plugin objects are stateful, so one deep copy per worker).  Returns (fitness, embeds, audios)."""
+    import copy
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import cnn14
+
+    if pad and x.shape[-1] <= 262144:
+        x = np.pad(x, ((0, 0), (0, 262144 - x.shape[-1])))
+    workers = max(1, min(len(W), os.cpu_count() or 1))
+    copies = [copy.deepcopy(oplugins) for _ in range(workers)]
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    fits, mids, sides, keep = [], [], [], []
+    for i in range(0, len(W), 8):
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            rendered = list(ex.map(lambda kw: oracle_dsp.process_audio(x, kw[1], SR, copies[kw[0] % workers]),
+                                   list(enumerate(W[i:i + 8]))))
+        audios = torch.stack([torch.from_numpy(a) for a in rendered])
+        if i == 0:
+            keep = audios.clone()
+        emb = cnn14.get_param_embeds(audios, ref, SR)
+        fits.append(cnn14.fitness(emb, te))
+        mids.append(emb["mid"])
+        sides.append(emb["side"])
+    return torch.cat(fits).numpy(), {"mid": torch.cat(mids).numpy(), "side": torch.cat(sides).numpy()}, keep
+
+
+def assert_population_parity(f, want, emb, oe):
+    """north_star gates: fitness / embeddings within 1e-4 relative, full argsort identical (pairs the ORACLE itself
+    separates by less than 1e-6 are near-ties, reported and excluded)."""
+    f, want = np.asarray(f, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    rel = np.abs(f - want) / np.maximum(np.abs(want), 1e-3)
+    assert rel.max() <= 1e-4, rel.max()
+    order = np.argsort(want, kind="stable")
+    gaps = np.diff(want[order])
+    near = int((gaps < 1e-6).sum())
+    if near == 0:
+        np.testing.assert_array_equal(np.argsort(f, kind="stable"), order)
+    else:  # same order wherever the oracle's own gap is resolvable
+        pos = np.empty(len(f), dtype=int)
+        pos[np.argsort(f, kind="stable")] = np.arange(len(f))
+        for a, b, g in zip(order[:-1], order[1:], gaps):
+            assert g < 1e-6 or pos[a] < pos[b]
+    assert int(np.argmin(f)) == int(order[0]) or gaps[0] < 1e-6
+    if emb is not None:
+        for k, e in zip(("mid", "side"), emb):
+            per_row = np.linalg.norm(e.numpy() - oe[k], axis=1) / np.linalg.norm(oe[k], axis=1)
+            assert per_row.max() < 1e-4, (k, per_row.max())
+    return rel.max(), near
+
+
+def test_config2_full_size_population_vs_oracle(models_centred, oracle_dsp):
+    """BASELINE config 2 exactly as stated: 10 s stereo 48 kHz (L = 480 000), EQ + Compressor + Reverb, P = 64,
+    tensor-core encoder -- fitness, embeddings and the FULL argsort against the CPU oracle; then config 3's shard
+    shape (P / G = 32): the second half of the same population evaluated alone is bit-identical to its rows."""
+    from oracle import cnn14
+    from st_ito_b200.engine import compile_chain
+
+    ours, ref = models_centred
+    eng = ours.stito_engine()
+    eng.set_precision(1)
+    kinds = ["eq", "comp", "reverb"]
+    plugins, D, _ = native_plugins(kinds)
+    oplugins, _, _ = oracle_plugins(oracle_dsp, kinds)
+    L, P = 480000, 64
+    x = test_signal(2, L, seed=0)
+    x = x / np.abs(x).max()
+    w_star = np.random.RandomState(1234).rand(D)
+    W = np.random.RandomState(2024).rand(P, D)
+    tgt = oracle_dsp.process_audio(x, w_star, SR, oplugins)
+    te = cnn14.get_param_embeds(torch.from_numpy(tgt[None].copy()), ref, SR)
+    want, oe, audios = oracle_population(oracle_dsp, x, W, oplugins, ref, te)
+
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    eng.set_input(x, min_len=262144)
+    eng.set_target_embeds(te["mid"][0], te["side"][0])
+    fit, emb, _ = eng.eval_population(W, 0, L, want_embeds=True)
+    err, near = assert_population_parity(fit.numpy(), want, emb, oe)
+    t = eng.timing()
+    assert t["precision"] == 1 and t["act_overflow"] == 0 and t["comp_fallbacks"] == 0
+    print(f"config2 P=64: max rel fitness err {err:.2e}, near-ties {near}, fitness spread {want.min():.3f}..{want.max():.3f}")
+    # config 3: 256 candidates over 8 GPUs = shards of 32; a shard scored alone equals its rows of the whole population
+    f_shard, e_shard, _ = eng.eval_population(W[32:], 0, L, want_embeds=True)
+    assert torch.equal(f_shard, fit[32:]) and torch.equal(e_shard, emb[:, 32:])
+    f8, _, aud8 = eng.eval_population(W[:8], 0, L, want_audio=True, in_chs=2)  # the 8-per-GPU shard of pop = 64 on 8 GPUs
+    assert torch.equal(f8, fit[:8])
+    assert np.abs(aud8.numpy() - audios.numpy()).max() <= 3e-5
+
+
+def test_config1_as_stated_vs_oracle(models_centred, oracle_dsp):
+    """BASELINE config 1 exactly: 5 s mono 48 kHz input + target, EQ-only chain, P = 8; evaluate() zero-pads to 262 144
+    samples (style_transfer.py:518).  Mono: side embedding = mid embedding (panns.py:271-274)."""
+    from oracle import cnn14
+    from st_ito_b200.engine import compile_chain
+
+    ours, ref = models_centred
+    eng = ours.stito_engine()
+    eng.set_precision(1)
+    plugins, D, _ = native_plugins(["eq"])
+    oplugins, _, _ = oracle_plugins(oracle_dsp, ["eq"])
+    L, P = 240000, 8
+    x = test_signal(1, L, seed=3)
+    x = x / np.abs(x).max()
+    rng = np.random.RandomState(8)
+    w_star, W = rng.rand(D), rng.rand(P, D)
+    tgt = oracle_dsp.process_audio(x, w_star, SR, oplugins)
+    te = cnn14.get_param_embeds(torch.from_numpy(tgt[None].copy()), ref, SR)
+    want, oe, _ = oracle_population(oracle_dsp, x, W, oplugins, ref, te)
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    eng.set_input(x, min_len=262144)
+    eng.set_target(tgt)
+    fit, emb, _ = eng.eval_population(W, 0, 262144, want_embeds=True)
+    assert_population_parity(fit.numpy(), want, emb, oe)
+    assert torch.equal(emb[0], emb[1])
+
+
+# ------------------------------------------------------------------------- written-but-untested code of round 1
+def test_savepop_through_the_fused_path(models_centred, tmp_path):
+    """savepop=True (style_transfer.py:362-396, 641-643): the fused evaluator returns every candidate's audio, the files
+    are written sorted by fitness, and each one equals process_audio of its candidate."""
+    from scipy.io import wavfile
+
+    from st_ito_b200.style_transfer import FusedEvaluator, process_audio, run_es, savepop_to_disk
+    from st_ito_b200.utils import get_param_embeds
+
+    ours, _ = models_centred
+    eng = ours.stito_engine()
+    eng.set_precision(1)
+    plugins, D, _ = native_plugins(["eq", "comp", "reverb"])
+    L = 70000
+    x = test_signal(2, L, seed=12)
+    x = x / np.abs(x).max()
+    tgt = test_signal(2, L, seed=13)
+    te = get_param_embeds(torch.from_numpy(tgt[None].copy()), ours, SR)
+    ev = FusedEvaluator(eng, plugins, SR, te, torch.from_numpy(x[None].copy()))
+    W = np.random.RandomState(6).rand(5, D)
+    fvals, embeds, audios = ev(W, want_audio=True, want_embeds=True)
+    assert audios.shape == (5, 2, 262144) and embeds["mid"].shape == (5, 512)
+    savepop_to_disk(0, fvals, embeds, audios, str(tmp_path), SR)
+    files = sorted(os.listdir(tmp_path / "pop_0"), key=lambda n: int(n.split("_")[3]))
+    assert len(files) == 5
+    order = np.argsort(fvals, kind="stable")
+    xpad = np.pad(x, ((0, 0), (0, 262144 - L)))
+    for k, name in enumerate(files):
+        assert abs(float(name.split("fval_")[1][:-4]) - fvals[order[k]]) <= 1e-4 * abs(fvals[order[k]]) + 1e-9
+        sr, y = wavfile.read(tmp_path / "pop_0" / name)
+        assert sr == SR
+        np.testing.assert_array_equal(y.T, process_audio(xpad, W[order[k]], SR, plugins))
+    # and through run_es itself: find_w0 population (pop_-1) + one folder per generation
+    res = run_es(torch.from_numpy(x[None].copy()), torch.from_numpy(tgt[None].copy()), SR, plugins, ours,
+                 get_param_embeds, max_iters=2, popsize=4, sigma0=0.33, find_w0=True, seed=1, verbose=False,
+                 savepop=True, run_dir=str(tmp_path / "run"))
+    assert sorted(os.listdir(tmp_path / "run")) == ["pop_-1", "pop_0", "pop_1"]
+    assert all(len(os.listdir(tmp_path / "run" / d)) == 4 for d in ("pop_-1", "pop_0", "pop_1"))
+    assert np.isfinite(res["fopt"])
+
+
+def test_dropout_branch_of_the_fused_path_equals_the_generic_loop(models_centred):
+    """dropout > 0 (style_transfer.py:550-551): F.dropout on the output embeddings draws from torch's global RNG in the
+    order mid, side -- the same draws as the reference-shaped generic loop, so with one torch seed the two paths give
+    the same stochastic fitness; and the last iteration runs without dropout (run_optim's convention, :634-636)."""
+    from st_ito_b200.style_transfer import run_es
+    from st_ito_b200.utils import get_param_embeds
+
+    ours, _ = models_centred
+    ours.stito_engine().set_precision(1)
+    x = test_signal(2, 50000, seed=31)
+    tgt = test_signal(2, 50000, seed=32)
+
+    def run(embed):
+        plugins, D, _ = native_plugins(["eq", "comp"])
+        torch.manual_seed(123)
+        return run_es(torch.from_numpy(x[None].copy()), torch.from_numpy(tgt[None].copy()), SR, plugins, ours, embed,
+                      max_iters=3, popsize=6, sigma0=0.33, find_w0=True, seed=2, verbose=False, dropout=0.3)
+
+    fused = run(get_param_embeds)
+    generic = run(lambda a, m, sr: get_param_embeds(a, m, sr))
+    np.testing.assert_array_equal(fused["wopt"], generic["wopt"])
+    np.testing.assert_allclose(fused["fval_history"][1:], generic["fval_history"][1:], rtol=0, atol=5e-5)
+    plugins, D, _ = native_plugins(["eq", "comp"])
+    torch.manual_seed(123)
+    plain = run_es(torch.from_numpy(x[None].copy()), torch.from_numpy(tgt[None].copy()), SR, plugins, ours,
+                   get_param_embeds, max_iters=3, popsize=6, sigma0=0.33, find_w0=True, seed=2, verbose=False)
+    assert plain["fval_history"][1:] != fused["fval_history"][1:]  # the regulariser really changed the fitness
+
+
+# --------------------------------------------------------------------------------------- numerics hardening
+def test_compressor_adversarial_corner_never_hands_out_an_unconverged_state(oracle_dsp):
+    """0.1 ms attack, 1 s release, -80 dB threshold, ratio 20 on an impulsive signal: the slowest case for the
+    time-parallel Newton iteration of compressor_scan_kernel.  Either it converges or the serial fallback runs
+    (stito_timing.comp_fallbacks counts it); the waveform must match the serial oracle either way."""
+    from st_ito_b200 import effects
+    from st_ito_b200.engine import fx_engine
+
+    L = 200000
+    rng = np.random.RandomState(3)
+    x = np.zeros((1, L), dtype=np.float32)
+    idx = rng.randint(0, L, 400)
+    x[0, idx] = rng.choice([-1.0, 1.0], 400) * rng.rand(400)
+    x[0] += 1e-4 * rng.randn(L)
+    x[0, 100000:100512] = 0.0
+    corners = [(0.0, 1.0, 0.0, 1.0), (0.0, 1.0, 1.0, 0.0), (1.0, 0.0, 0.0, 0.0), (0.5, 1.0, 0.0, 0.0), (0.0, 1.0, 0.0, 0.3)]
+    total_fallbacks = 0
+    for raw in corners:
+        ours = effects.BasicCompressor()
+        ref = oracle_dsp.OracleCompressor()
+        for p, v in zip(ours.parameters.values(), raw):
+            p.raw_value = v
+        for p, v in zip(ref.parameters.values(), raw):
+            p.raw_value = v
+        y = ours.process(x.copy(), SR)
+        want = ref.process(x.copy(), SR)
+        peak = max(np.abs(want).max(), 1e-8)
+        assert np.abs(y - want).max() <= 5e-6 * peak, (raw, np.abs(y - want).max() / peak)
+        total_fallbacks += fx_engine().timing()["comp_fallbacks"]
+    print("compressor serial fallbacks over the corner cases:", total_fallbacks)
+
+
+def test_fp16_range_guard_recalibrates_the_activation_scales(oracle_dsp):
+    """activations above ~1023 would become inf/NaN in fixed 2^6-scaled fp16 hi/lo pairs and the NaN scrub
+    would turn that into a plausible-looking fitness.  The per-layer scales are calibrated from measured maxima: with
+    BatchNorm scales that push block-2 activations to ~1e5 (and back down in the next layer) the tensor-core path
+    must stay in use and match the oracle."""
+    from oracle import cnn14
+    from st_ito_b200.engine import compile_chain
+    from st_ito_b200.utils import make_synthetic_param_model
+
+    ours = make_synthetic_param_model(seed=5, bn_stats=True, conv_gain=2.0)
+    ref = cnn14.make_encoder(seed=5, bn_stats=True, conv_gain=2.0)
+    with torch.no_grad():
+        for m in (ours, ref):
+            m.conv_block2.bn1.weight.mul_(3.0e4)        # huge activations after block 2 conv 1 ...
+            m.conv_block2.bn1.bias.mul_(3.0e4)
+            m.conv_block2.conv2.weight.mul_(1.0 / 3.0e4)  # ... scaled back by the next layer
+            m.conv_block4.bn2.weight.mul_(1.0e-4)        # and tiny ones after block 4 (fixed scaling: lo parts subnormal)
+            m.conv_block4.bn2.bias.mul_(1.0e-4)
+            m.conv_block5.conv1.weight.mul_(1.0e4)
+    cnn14.centre_heads(ref)
+    with torch.no_grad():
+        ours.fc_mid.bias.copy_(ref.fc_mid.bias)
+        ours.fc_side.bias.copy_(ref.fc_side.bias)
+    eng = ours.stito_engine()
+    eng.set_precision(1)
+    plugins, D, _ = native_plugins(["eq"])
+    oplugins, _, _ = oracle_plugins(oracle_dsp, ["eq"])
+    L = 60000
+    x = test_signal(2, L, seed=4)
+    x = x / np.abs(x).max()
+    rng = np.random.RandomState(1)
+    w_star, W = rng.rand(D), rng.rand(3, D)
+    tgt = oracle_dsp.process_audio(x, w_star, SR, oplugins)
+    te = cnn14.get_param_embeds(torch.from_numpy(tgt[None].copy()), ref, SR)
+    audios = torch.stack([torch.from_numpy(oracle_dsp.process_audio(x, w, SR, oplugins)) for w in W])
+    want = cnn14.fitness(cnn14.get_param_embeds(audios, ref, SR), te).numpy()
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    eng.set_input(x)
+    eng.set_target_embeds(te["mid"][0], te["side"][0])
+    fit, _, _ = eng.eval_population(W, 0, L)
+    t = eng.timing()
+    assert t["act_overflow"] >= 1 and t["precision"] == 1, t
+    assert np.all(np.abs(fit.numpy() - want) <= 1e-4 * np.maximum(np.abs(want), 1e-3)), (fit, want)
+    fit2, _, _ = eng.eval_population(W, 0, L)  # calibrated: one pass, same bits
+    assert eng.timing()["act_overflow"] == 0 and eng.timing()["precision"] == 1 and torch.equal(fit, fit2)
+    ours.stito_engine().close()
+
+
+def test_empty_shard_is_a_noop(models_centred):
+    """more ranks than candidates leaves trailing ranks with P = 0; the C ABI accepts it."""
+    from st_ito_b200.engine import compile_chain
+
+    ours, _ = models_centred
+    eng = ours.stito_engine()
+    plugins, D, _ = native_plugins(["eq"])
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    x = test_signal(1, 40000, seed=9)
+    eng.set_input(x)
+    eng.set_target(x)
+    fit, emb, _ = eng.eval_population(np.zeros((0, D)), 0, 40000, want_embeds=True)
+    assert fit.shape == (0,) and emb.shape == (2, 0, 512)
+    fit, _, _ = eng.eval_population(np.zeros((0, D)), 0, 40000, device_out=True)
+    assert fit.shape == (0,) and fit.is_cuda
+
+
+@pytest.mark.parametrize("fixture", ["xavier", "heavy"])
+@pytest.mark.parametrize("comp", [None, "0"])
+def test_encoder_gate_on_a_second_weight_distribution(fixture, comp):
+    """the compensation of the tensor core's truncating accumulate (1 + 0.25 * 2^-24 per MMA step)
+    was fitted on one Xavier-uniform fixture.  The 1e-4 embedding gate must hold (a) on a second distribution --
+    heavy-tailed weights, BatchNorm scales near zero and large (tests/dev/dev_margins2.py) -- and (b) with the
+    compensation switched off (STITO_TC_COMP=0), i.e. the gate may not DEPEND on the fitted constant.  The knob is read
+    once per process, hence the subprocess."""
+    import json
+    import subprocess
+    import sys
+
+    env = dict(os.environ)
+    env.pop("STITO_TC_COMP", None)
+    if comp is not None:
+        env["STITO_TC_COMP"] = comp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "dev", "dev_margins2.py"), fixture], env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    print(res)
+    assert res["precision"] == 1 and res["act_overflow"] == 0
+    for tag, errs in res["err"].items():
+        assert max(errs) < 1e-4, (fixture, comp, tag, errs)
+    assert res["fit_err"] < 1e-4
