@@ -43,7 +43,7 @@ extern "C" {
 #define STITO_ENOMEM (-4)
 
 #define STITO_MAX_FX 8
-#define STITO_MAX_FX_PARAMS 24
+#define STITO_MAX_FX_PARAMS 32
 #define STITO_EMBED_DIM_MAX 1024
 
 /* Effects of the reference's built-in ("Basic*") plugin family, st_ito/effects.py:800-959. */
@@ -52,7 +52,12 @@ enum stito_fx_kind {
     STITO_FX_COMPRESSOR = 1, /* BasicCompressor    effects.py:876-897 (4)                        */
     STITO_FX_DISTORTION = 2, /* BasicDistortion    effects.py:900-914 (2)                        */
     STITO_FX_DELAY = 3,      /* BasicDelay         effects.py:917-934 (3)                        */
-    STITO_FX_REVERB = 4      /* BasicReverb        effects.py:937-959 (4)                        */
+    STITO_FX_REVERB = 4,     /* BasicReverb        effects.py:937-959 (4)                        */
+    /* Noise-shaped convolution reverb: the arithmetic of apply_reverb, effects.py:558-620 -> dasp-pytorch's
+     * noise_shaped_reverberation (25 parameters used raw: 12 band gains, 12 band decays, mix); num_channels must be 2.
+     * iopt[0] = impulse-response length in samples (65536 = dasp default; 96000 = the 2 s IR of BASELINE config 4),
+     * iopt[1] = seed of the white noise (the reference draws fresh noise per call; here it is fixed per plugin). */
+    STITO_FX_CONV_REVERB = 5
 };
 
 /* One entry of the reference's ordered `plugins` dict (run_optim.py:376-407,
@@ -65,6 +70,7 @@ typedef struct {
     int32_t num_params;                       /* effect parameters described below (excl. our_bypass) */
     int32_t w_index[STITO_MAX_FX_PARAMS];     /* index into w, or -1: use fixed_raw                   */
     double fixed_raw[STITO_MAX_FX_PARAMS];    /* raw_value of fixed_parameters (Parameter.set_value)  */
+    int32_t iopt[4];                          /* per-kind integer options (see enum stito_fx_kind)    */
 } stito_fx_desc;
 
 typedef struct {

@@ -196,12 +196,16 @@ class OracleReverb:
 # --------------------------------------------------------------------------
 def make_plugins(kinds, channels=None, fixed=None):
     """Build a reference-style plugins dict from effect kinds, e.g. ("eq","comp","reverb")."""
+    from oracle.convreverb import OracleNoiseShapedReverb, OracleNoiseShapedReverb2s
+
     table = {
         "eq": ("ParametricEQ", OracleParametricEQ, 1),
         "comp": ("Compressor", OracleCompressor, 1),
         "dist": ("Distortion", OracleDistortion, 1),
         "delay": ("Delay", OracleDelay, 2),
         "reverb": ("Reverb", OracleReverb, 2),
+        "convreverb": ("NoiseShapedReverb", OracleNoiseShapedReverb, 2),      # 65 536-tap IR (dasp default)
+        "convreverb2s": ("NoiseShapedReverb", OracleNoiseShapedReverb2s, 2),  # 96 000-tap IR (BASELINE config 4)
     }
     plugins = {}
     for i, k in enumerate(kinds):

@@ -17,9 +17,9 @@ LIB_PATH = os.path.join(_HERE, "libstito.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MAX_FX = 8
-MAX_FX_PARAMS = 24
+MAX_FX_PARAMS = 32
 
-FX_EQ, FX_COMPRESSOR, FX_DISTORTION, FX_DELAY, FX_REVERB = range(5)
+FX_EQ, FX_COMPRESSOR, FX_DISTORTION, FX_DELAY, FX_REVERB, FX_CONV_REVERB = range(6)
 
 
 class FxDesc(Structure):
@@ -29,6 +29,7 @@ class FxDesc(Structure):
         ("num_params", c_int32),
         ("w_index", c_int32 * MAX_FX_PARAMS),
         ("fixed_raw", c_double * MAX_FX_PARAMS),
+        ("iopt", c_int32 * 4),
     ]
 
 

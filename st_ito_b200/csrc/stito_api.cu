@@ -86,6 +86,9 @@ const Range kCompRanges[4] = {{-80, 0}, {1, 20}, {0.1, 100}, {10, 1000}};
 const Range kDistRanges[2] = {{-48, 48}, {-24, 24}};
 const Range kDelayRanges[3] = {{0.01, 1.0}, {0.05, 1.0}, {0.0, 1.0}};
 const Range kReverbRanges[4] = {{0, 1}, {0, 1}, {0, 1}, {0, 1}};
+const Range kUnitRanges[STITO_MAX_FX_PARAMS] = {{0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1},
+                                                {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1},
+                                                {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}};
 
 int fx_num_params(int kind) {
     switch (kind) {
@@ -94,6 +97,7 @@ int fx_num_params(int kind) {
         case STITO_FX_DISTORTION: return 2;
         case STITO_FX_DELAY: return 3;
         case STITO_FX_REVERB: return 4;
+        case STITO_FX_CONV_REVERB: return 25;
     }
     return -1;
 }
@@ -104,6 +108,7 @@ const Range *fx_ranges(int kind) {
         case STITO_FX_DISTORTION: return kDistRanges;
         case STITO_FX_DELAY: return kDelayRanges;
         case STITO_FX_REVERB: return kReverbRanges;
+        case STITO_FX_CONV_REVERB: return kUnitRanges;
     }
     return nullptr;
 }
@@ -181,6 +186,7 @@ struct stito_handle {
     int tc_attempts = 0;
     int comp_fallbacks_total = 0;
     ReverbGeom rgeom{};
+    ConvReverbState crv;
     TcWorkspace tcws;
 
     // timing
@@ -248,6 +254,11 @@ int validate_chain(const stito_chain_desc *c) {
         if (np < 0) return fail(STITO_EINVAL, "effect %d: unknown kind %d", f, d.kind);
         if (d.num_params != np) return fail(STITO_EINVAL, "effect %d: kind %d takes %d parameters, got %d", f, d.kind, np, d.num_params);
         if (d.num_channels != 1 && d.num_channels != 2) return fail(STITO_EINVAL, "effect %d: num_channels must be 1 or 2", f);
+        if (d.kind == STITO_FX_CONV_REVERB) {
+            if (d.num_channels != 2) return fail(STITO_EINVAL, "effect %d: the convolution reverb is a 2-channel plugin", f);
+            if (d.iopt[0] < 2 || d.iopt[0] > 131072) return fail(STITO_EINVAL, "effect %d: impulse-response length %d outside [2, 131072]", f, d.iopt[0]);
+            if (c->sample_rate < 36100.0) return fail(STITO_EINVAL, "effect %d: the 18 kHz band of the convolution reverb needs a sample rate above 36.1 kHz", f);
+        }
         for (int k = 0; k < np; ++k)
             if (d.w_index[k] >= c->num_w) return fail(STITO_EINVAL, "effect %d parameter %d: w index %d >= D=%d", f, k, d.w_index[k], c->num_w);
     }
@@ -318,6 +329,12 @@ void design_params(const stito_chain_desc &c, const double *W, int P, int D, uin
                     q->mix = (float)v[2];
                     q->dry = 1.0f - q->mix;
                     if (dd > *max_d) *max_d = dd;
+                    break;
+                }
+                case STITO_FX_CONV_REVERB: {  // apply_reverb (effects.py:564-588): parameters are used raw
+                    ConvRevParams *q = reinterpret_cast<ConvRevParams *>(block) + p;
+                    for (int b = 0; b < 12; ++b) { q->gain[b] = (float)v[b]; q->decay[b] = (float)v[12 + b]; }
+                    q->mix = (float)v[24];
                     break;
                 }
                 case STITO_FX_REVERB: {  // BasicReverb.process (effects.py:952-959) + oracle_reverb
@@ -404,6 +421,11 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
             case STITO_FX_DELAY:
                 CU(launch_delay(st, cur, in_peak, out, P, cur_chs, L, reinterpret_cast<const DelayParams *>(slot), max_d, opk, launches));
                 break;
+            case STITO_FX_CONV_REVERB: {
+                CU(convreverb_prepare(st, &h->crv, c.sample_rate, d.iopt[0], d.iopt[1]));
+                CU(launch_convreverb(st, &h->crv, cur, in_peak, out, P, L, reinterpret_cast<const ConvRevParams *>(slot), opk, launches));
+                break;
+            }
             case STITO_FX_REVERB: {
                 const int stereo = (cur_chs == 2 && d.num_channels == 2) ? 1 : 0;
                 cudaError_t e = launch_reverb(st, cur, in_peak, out, P, cur_chs, stereo, L, h->rgeom,
@@ -615,6 +637,7 @@ void stito_destroy(stito_handle *h) {
     h->hW.release();
     h->hflags.release();
     tc_workspace_release(&h->tcws);
+    convreverb_release(&h->crv);
     for (int i = 0; i < kNumEvents; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 13; ++i) if (h->ev_conv[i]) cudaEventDestroy(h->ev_conv[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -27,6 +27,7 @@ struct CompParams { float cte_at, cte_rl, thr, thr_inv, expo; };
 struct DistParams { float drive, out_gain; };
 struct DelayParams { int d; float feedback, mix, dry; };
 struct ReverbParams { float damp, fb, wet1, wet2, dry; };
+struct ConvRevParams { float gain[12]; float decay[12]; float mix; };  // raw [0, 1] values (effects.py:564-588)
 struct ReverbGeom {
     int comb_size[2][8], comb_off[2][8];
     int ap_size[2][4], ap_off[2][4];
@@ -65,6 +66,23 @@ cudaError_t launch_peak(cudaStream_t st, SigView in, int P, int chs, int64_t L, 
 cudaError_t launch_normalize(cudaStream_t st, const float *x, const unsigned *peak, float *y, int P,
                              int chs, int64_t L, int *launches);
 void reverb_geometry(double sample_rate, ReverbGeom *g);
+
+// Noise-shaped convolution reverb (convreverb.cu).  The state caches what does not depend on the candidate -- the
+// filtered-noise bands of (sample rate, IR length, seed) and the FFT twiddles -- plus the spectra work buffers.
+struct ConvReverbState {
+    float *bands = nullptr;     // [2][12][n_ir]
+    float2 *twiddle = nullptr;  // [16384]
+    float4 *H = nullptr;        // [P][K][8193] candidate IR spectra
+    float2 *X = nullptr;        // [P][blocks][16384] input / output spectra
+    size_t H_cap = 0, X_cap = 0;
+    int n_ir = 0, seed = 0;
+    double sample_rate = 0.0;
+};
+cudaError_t convreverb_prepare(cudaStream_t st, ConvReverbState *s, double sample_rate, int n_ir, int seed);
+// in: stereo view (mono is up-mixed by stride_c == 0); out [P][2][L]
+cudaError_t launch_convreverb(cudaStream_t st, ConvReverbState *s, SigView in, const float *in_peak, float *out, int P,
+                              int64_t L, const ConvRevParams *prm, unsigned *out_peak, int *launches);
+void convreverb_release(ConvReverbState *s);
 
 // ------------------------------------------------------- front-end (frontend_kernels.cu)
 struct FrontendTables {

@@ -14,6 +14,8 @@ Arithmetic notes (what the kernels implement; the CPU restatement used by the te
   * BasicDistortion     pedalboard.Distortion (tanh) + pedalboard.Gain            [recollection]
   * BasicDelay          pedalboard.Delay (whole-sample feedback delay, dry/wet)   [recollection]
   * BasicReverb         pedalboard.Reverb = juce::Reverb (Freeverb)               [recollection]
+  * BasicNoiseShapedReverb  the convolution reverb of apply_reverb (effects.py:558-620) =
+                        dasp_pytorch.noise_shaped_reverberation                   [recollection]
 """
 from __future__ import annotations
 
@@ -130,6 +132,42 @@ class BasicReverb(_BasicPlugin):
         self._init_parameters([room_size, damping, wet_dry, width])
 
 
+def _nsr_spec():
+    spec = [(f"band{b}_gain", 1.0, 0.0, 1.0) for b in range(12)]
+    spec += [(f"band{b}_decay", d, 0.0, 1.0)
+             for b, d in enumerate((0.6, 0.4, 0.4, 0.5, 0.2, 0.3, 0.3, 0.2, 0.1, 0.1, 0.2, 0.1))]  # dsp.py:28-30
+    return tuple(spec + [("mix", 0.5, 0.0, 1.0)])
+
+
+class BasicNoiseShapedReverb(_BasicPlugin):
+    """Convolution reverb with a noise-shaped impulse response, in the plugin protocol of the ES path.
+
+    The reference reaches this effect only through ``apply_reverb`` (effects.py:558-620, run_autodiff) and
+    ``apply_random_reverb`` (dsp.py:26-46); BASELINE config 4 puts it on the ES path ("2 s-IR conv reverb").  The 25
+    parameters are the ones of effects.py:564-588 (12 band gains, 12 band decays, mix), all used raw on [0, 1].
+    ``num_samples`` is the impulse-response length (65 536 = dasp-pytorch's default), ``seed`` fixes the white noise
+    that the reference re-draws on every call (see libstito / oracle/convreverb.py).  A 2-channel plugin.
+    """
+
+    stito_kind = _lib.FX_CONV_REVERB
+    _spec = _nsr_spec()
+
+    def __init__(self, num_samples: int = 65536, seed: int = 0):
+        self.num_samples, self.seed = int(num_samples), int(seed)
+        self._init_parameters([s[1] for s in self._spec])
+
+    @property
+    def stito_iopt(self):
+        return (self.num_samples, self.seed, 0, 0)
+
+
+class BasicNoiseShapedReverb2s(BasicNoiseShapedReverb):
+    """BASELINE config 4: a 2 s impulse response (96 000 taps at 48 kHz)."""
+
+    def __init__(self):
+        super().__init__(num_samples=96000, seed=0)
+
+
 def is_native_plugin(obj) -> bool:
     """True for plugins libstito can render (their ranges are the ones compiled into the library)."""
     if not isinstance(obj, _BasicPlugin) or obj.stito_kind < 0:
@@ -147,11 +185,13 @@ def make_chain(kind: str = "basic") -> dict:
     table = {
         "ParametricEQ": (BasicParametricEQ, 1), "Compressor": (BasicCompressor, 1),
         "Distortion": (BasicDistortion, 1), "Delay": (BasicDelay, 2), "Reverb": (BasicReverb, 2),
+        "NoiseShapedReverb": (BasicNoiseShapedReverb2s, 2),
     }
     presets = {
         "basic": ["ParametricEQ", "Compressor", "Distortion", "Delay", "Reverb"],
         "mastering-pb": ["ParametricEQ", "Compressor", "Reverb"],
         "eq": ["ParametricEQ"],
+        "mastering-conv": ["ParametricEQ", "Compressor", "NoiseShapedReverb"],  # BASELINE config 4
     }
     if kind not in presets:
         raise ValueError(f"Unknown chain: {kind}")

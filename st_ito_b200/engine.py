@@ -90,6 +90,8 @@ def compile_chain(plugins: dict, sample_rate: float, normalize_stages: bool = Fa
         fx = desc.fx[f]
         fx.kind = inst.stito_kind
         fx.num_channels = int(plugin["num_channels"])
+        for k, v in enumerate(getattr(inst, "stito_iopt", (0, 0, 0, 0))):
+            fx.iopt[k] = int(v)
         names = [s[0] for s in inst._spec]
         fx.num_params = len(names)
         for k in range(_lib.MAX_FX_PARAMS):
@@ -119,7 +121,9 @@ def _single_plugin_chain(plugin, chs: int, sample_rate: float):
     desc.sample_rate = float(sample_rate)
     fx = desc.fx[0]
     fx.kind = plugin.stito_kind
-    fx.num_channels = chs
+    fx.num_channels = 2 if plugin.stito_kind == _lib.FX_CONV_REVERB else chs  # always a stereo effect (mono is up-mixed)
+    for k, v in enumerate(getattr(plugin, "stito_iopt", (0, 0, 0, 0))):
+        fx.iopt[k] = int(v)
     fx.num_params = len(plugin._spec)
     for k, (n, *_rest) in enumerate(plugin._spec):
         fx.w_index[k] = -1

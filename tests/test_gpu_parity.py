@@ -64,7 +64,9 @@ def native_plugins(kinds, load=True):
 
     table = {"eq": ("ParametricEQ", effects.BasicParametricEQ, 1), "comp": ("Compressor", effects.BasicCompressor, 1),
              "dist": ("Distortion", effects.BasicDistortion, 1), "delay": ("Delay", effects.BasicDelay, 2),
-             "reverb": ("Reverb", effects.BasicReverb, 2)}
+             "reverb": ("Reverb", effects.BasicReverb, 2),
+             "convreverb": ("NoiseShapedReverb", effects.BasicNoiseShapedReverb, 2),
+             "convreverb2s": ("NoiseShapedReverb", effects.BasicNoiseShapedReverb2s, 2)}
     plugins = {}
     for k in kinds:
         name, cls, ch = table[k]
@@ -900,3 +902,89 @@ def test_encoder_gate_on_a_second_weight_distribution(fixture, comp):
     for tag, errs in res["err"].items():
         assert max(errs) < 1e-4, (fixture, comp, tag, errs)
     assert res["fit_err"] < 1e-4
+
+
+# ------------------------------------------------------------- noise-shaped convolution reverb
+@pytest.mark.parametrize("chs", [1, 2])
+@pytest.mark.parametrize("num_samples,L", [(65536, 100000), (20000, 50001), (96000, 131072 + 7)])
+def test_noise_shaped_reverb_matches_oracle(chs, num_samples, L):
+    """apply_reverb's arithmetic (effects.py:558-620 -> dasp noise_shaped_reverberation) as an ES-path plugin: the
+    partitioned FFT convolution against oracle/convreverb.py (scipy firwin + float64 FFT convolution).  The oracle is
+    parity-unpinned (dasp-pytorch is absent upstream); the white noise is the seeded generator both sides restate."""
+    from oracle import convreverb
+    from st_ito_b200 import effects
+
+    rng = np.random.RandomState(num_samples + chs)
+    x = test_signal(chs, L, seed=90 + chs)
+    ours = effects.BasicNoiseShapedReverb(num_samples=num_samples, seed=7)
+    ref = convreverb.OracleNoiseShapedReverb(num_samples=num_samples, seed=7)
+    for trial in range(3):
+        raw = rng.rand(25) if trial else np.array([1.0] * 12 + [0.0] * 12 + [1.0])  # trial 0: full gain, slowest decay, all wet
+        for p, q, v in zip(ours.parameters.values(), ref.parameters.values(), raw):
+            p.raw_value = float(v)
+            q.raw_value = float(v)
+        y = ours.process(x.copy(), SR)
+        want = ref.process(x.copy(), SR)
+        assert y.shape == want.shape == (2, L) and y.dtype == np.float32
+        peak = np.abs(want).max()
+        assert np.abs(y - want).max() <= 1e-5 * peak, (trial, np.abs(y - want).max() / peak)
+
+
+def test_conv_reverb_chain_population_vs_oracle(models_centred, oracle_dsp):
+    """EQ -> Compressor -> 2 s-IR convolution reverb (BASELINE config 4's chain, D = 50) through evaluate()."""
+    from oracle import cnn14
+    from st_ito_b200.engine import compile_chain
+
+    ours, ref = models_centred
+    eng = ours.stito_engine()
+    eng.set_precision(1)
+    kinds = ["eq", "comp", "convreverb2s"]
+    plugins, D, _ = native_plugins(kinds)
+    oplugins, oD, _ = oracle_plugins(oracle_dsp, kinds)
+    assert D == oD == 50
+    L, P = 300000, 6
+    x = test_signal(2, L, seed=61)
+    x = x / np.abs(x).max()
+    rng = np.random.RandomState(62)
+    w_star, W = rng.rand(D), rng.rand(P, D)
+    tgt = oracle_dsp.process_audio(x, w_star, SR, oplugins)
+    te = cnn14.get_param_embeds(torch.from_numpy(tgt[None].copy()), ref, SR)
+    want, oe, audios = oracle_population(oracle_dsp, x, W, oplugins, ref, te, pad=False)
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    eng.set_input(x)
+    eng.set_target_embeds(te["mid"][0], te["side"][0])
+    fit, emb, aud = eng.eval_population(W, 0, L, want_embeds=True, want_audio=True, in_chs=2)
+    assert_population_parity(fit.numpy(), want, emb, oe)
+    assert np.abs(aud.numpy() - audios.numpy()).max() <= 2e-5
+
+
+def test_config4_as_stated_30s_conv_reverb(models_centred, oracle_dsp):
+    """BASELINE config 4: 30 s stereo (L = 1 440 000), 6-band EQ + compressor + 2 s-IR convolution reverb."""
+    from st_ito_b200.engine import compile_chain
+    from st_ito_b200.style_transfer import process_audio
+
+    ours, _ = models_centred
+    eng = ours.stito_engine()
+    eng.set_precision(1)
+    kinds = ["eq", "comp", "convreverb2s"]
+    plugins, D, _ = native_plugins(kinds)
+    oplugins, _, _ = oracle_plugins(oracle_dsp, kinds)
+    L = 1440000
+    x = test_signal(2, L, seed=33)
+    x = x / np.abs(x).max()
+    rng = np.random.RandomState(45)
+    w_star = rng.rand(D)
+    W = rng.rand(3, D)
+    W[2] = w_star
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    eng.set_input(x)
+    tgt = process_audio(x, w_star, SR, plugins)
+    eng.set_target(tgt)
+    fit, _, aud = eng.eval_population(W, 0, L, want_audio=True, in_chs=2)
+    assert abs(fit[2].item() + 1.0) < 1e-5 and int(torch.argmin(fit)) == 2
+    ref0 = oracle_dsp.process_audio(x, W[0], SR, oplugins)
+    err = np.abs(aud[0].numpy() - ref0)
+    assert err.max() <= 3e-5 and err.mean() <= 5e-6, (err.max(), err.mean())
+    np.testing.assert_array_equal(aud[2].numpy(), tgt)
