@@ -171,6 +171,23 @@ STITO_API int stito_logmel(stito_handle *h, const float *x, int B, int chs, int6
 
 STITO_API int stito_get_timing(const stito_handle *h, stito_timing *out);
 
+/* ---- native CMA-ES (host, fp64): what run_es obtains from pycma, style_transfer.py:614-673 -----------------------------
+ * cma.CMAEvolutionStrategy(x0, sigma0, {"bounds": [lower, upper], "popsize": P}) -> stito_cma_create (lower >= upper: no
+ * bounds); es.ask() -> stito_cma_ask (X [P][D], feasible); es.tell(X, f) -> stito_cma_tell; es.result -> stito_cma_result.
+ * (mu/mu_w, lambda)-CMA-ES, rank-one + rank-mu update, CSA, pycma's BoxConstraintsLinQuadTransformation.  Gaussian
+ * draws: element n of the stream = Box-Muller (cos, sin branches alternate) of the uniforms splitmix64(key + 2m),
+ * splitmix64(key + 2m + 1), key = splitmix64(seed).  These return STITO_E* codes and set no message. */
+typedef struct stito_cma stito_cma;
+STITO_API int stito_cma_create(const double *x0, int D, double sigma0, int popsize, double lower, double upper,
+                               uint64_t seed, stito_cma **out);
+STITO_API void stito_cma_destroy(stito_cma *es);
+STITO_API int stito_cma_eig(const double *A, int n, double *V, double *d); /* symmetric eigensolver of the update (tests) */
+STITO_API int stito_cma_ask(stito_cma *es, double *X);
+STITO_API int stito_cma_tell(stito_cma *es, const double *X, const double *f);
+STITO_API int stito_cma_result(const stito_cma *es, double *xbest, double *fbest, int *has_best, double *xfavorite,
+                               double *sigma, double *stds, int64_t *evals_best, int64_t *evaluations,
+                               int64_t *iterations, double *axis_ratio, double *last_f_range);
+
 /* Thread-local message of the last failing call. */
 STITO_API const char *stito_last_error(void);
 

@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstito.so")
@@ -94,6 +94,12 @@ EXPORTS = {
     "stito_embed": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "stito_logmel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),
     "stito_get_timing": (c_int, [c_void_p, POINTER(Timing)]),
+    "stito_cma_create": (c_int, [c_void_p, c_int, c_double, c_int, c_double, c_double, c_uint64, POINTER(c_void_p)]),
+    "stito_cma_destroy": (None, [c_void_p]),
+    "stito_cma_eig": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "stito_cma_ask": (c_int, [c_void_p, c_void_p]),
+    "stito_cma_tell": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "stito_cma_result": (c_int, [c_void_p] + [c_void_p] * 11),
     "stito_last_error": (c_char_p, []),
     "stito_version": (c_int, []),
 }

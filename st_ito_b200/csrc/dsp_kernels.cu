@@ -17,6 +17,7 @@
 //   delay       lag-d feedback: the d residue classes are independent serial chains.
 // All float arithmetic uses explicit _rn intrinsics where the oracle (compiled with
 // -ffp-contract=off) rounds each operation separately.
+#include <cstdio>
 #include <cstdlib>
 
 #include "stito_internal.h"
@@ -37,6 +38,32 @@ __device__ __forceinline__ float clip_peak(const float *in_peak, int p) {
 __device__ __forceinline__ void atomic_peak(unsigned *peak, int p, float v) {
     // v >= 0: IEEE ordering of non-negative floats equals unsigned ordering of their bits
     if (v > 0.0f) atomicMax(peak + p, __float_as_uint(v));
+}
+
+// ---- streaming hand-off between two concurrently resident kernels (small populations: see run_chain in stito_api.cu)
+// The producer publishes one flag per (stream, granule of 2^kGranuleShift samples) once that part of its output is in
+// global memory; the consumer, which walks time in order, polls the flag of the next granule it needs.
+constexpr int kGranuleShift = 15;  // 32768 samples = one compressor super-block
+
+__device__ __forceinline__ void publish_granule(int *flags, int idx) {  // one thread, after a CTA barrier
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + idx), "r"(1) : "memory");
+}
+__device__ __forceinline__ void await_granule(const int *flags, int idx) {  // one thread; bounded: a lost producer must
+    int v = 0;                                                                // fail loudly, never hang the GPU
+    unsigned long long t0 = 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + idx) : "memory");
+        if (v != 0) return;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t0 == 0) t0 = t1;
+        if (t1 - t0 > 4000000000ull) {  // 4 s
+            printf("libstito: streaming hand-off timeout (block %d flag %d)\n", blockIdx.x, idx);
+            __trap();
+        }
+        __nanosleep(200);
+    }
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -254,7 +281,7 @@ constexpr size_t kCsSmem = (size_t)(kCsT * kCsPitch + 2 * kCsT + 2 * (kCsT / 32)
 
 __global__ void __launch_bounds__(kCsT, 1) compressor_scan_kernel(SigView in, const float *in_peak, float *out,
                                                                    int chs, int64_t L, const CompParams *prm,
-                                                                   unsigned *out_peak, int *noconv) {
+                                                                   unsigned *out_peak, int *noconv, int *ready) {
     extern __shared__ float cs_sm[];
     float *xs = cs_sm;                       // [kCsT][kCsPitch] samples, later overwritten by the output
     float *sout_s = xs + kCsT * kCsPitch;    // [kCsT] outgoing state of each chunk
@@ -416,6 +443,9 @@ __global__ void __launch_bounds__(kCsT, 1) compressor_scan_kernel(SigView in, co
             for (int idx = t; idx < nb; idx += kCsT) dst[b0 + idx] = xs[(idx >> 6) * kCsPitch + (idx & 63)];
         }
         __syncthreads();
+        // streaming: this super-block of the output is complete -> the reverb CTA of this stream may consume it
+        if (ready != nullptr && t == 0)
+            publish_granule(ready, stream * (int)((L + kCsSB - 1) / kCsSB) + (int)(b0 / kCsSB));
     }
     if (out_peak != nullptr) {
         pk = warp_max(pk);
@@ -671,7 +701,8 @@ __device__ __forceinline__ void cluster_barrier() {
 template <int SEG, bool PAIR>
 __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in, const float *in_peak, float *out,
                                                                      int chs, int64_t L, ReverbFastGeom g,
-                                                                     const ReverbParams *prm, unsigned *out_peak) {
+                                                                     const ReverbParams *prm, unsigned *out_peak,
+                                                                     const int *ready) {
     extern __shared__ float sm[];
     float *comb = sm;                        // [8][kCombRing]
     float *ap = sm + 8 * kCombRing;          // [4][kApRing]
@@ -712,10 +743,28 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
         for (int k = 0; k < kPre; ++k) {
             const int64_t n = base + tid + k * kRevThreads;
             const bool ok = (tid + k * kRevThreads) < S && n < L;
-            pl[k] = ok ? load_in(in, p, PAIR ? 0 : c, n) : 0.0f;
-            pr[k] = (ok && PAIR) ? load_in(in, p, 1, n) : 0.0f;
+            // ld.cg, not the read-only path: in streaming mode the producer kernel is still writing this buffer
+            pl[k] = ok ? __ldcg(in.base + (int64_t)p * in.stride_p + (int64_t)(PAIR ? 0 : c) * in.stride_c + n) : 0.0f;
+            pr[k] = (ok && PAIR) ? __ldcg(in.base + (int64_t)p * in.stride_p + in.stride_c + n) : 0.0f;
         }
     };
+    // streaming consumer state: samples [0, avail) of my input stream(s) are known to be complete
+    constexpr int S_ = 32 * SEG;
+    const int ngran = (int)((L + (1 << kGranuleShift) - 1) >> kGranuleShift);
+    int64_t avail = ready != nullptr ? 0 : L;
+    auto need_input = [&](int64_t upto) {  // tid 0 only; followed by a CTA barrier before anybody loads
+        upto = min(upto, L);
+        while (avail < upto) {
+            const int gidx = (int)(avail >> kGranuleShift);
+            if (PAIR) { await_granule(ready, (p * 2) * ngran + gidx); await_granule(ready, (p * 2 + 1) * ngran + gidx); }
+            else await_granule(ready, inst * ngran + gidx);
+            avail += (1 << kGranuleShift);
+        }
+    };
+    if (ready != nullptr) {
+        if (tid == 0) need_input(2 * (int64_t)S_);
+        __syncthreads();
+    }
     {
         float pl[kPre], pr[kPre];
         fetch(pl, pr, 0);
@@ -856,6 +905,7 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
                 asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_bar + 8u * (uint32_t)(step & 1)) : "memory");
         }
         park(pre_l, pre_r, ib == 2 ? 0 : ib + 1);
+        if (ready != nullptr && tid == 0) need_input(n0 + 3 * (int64_t)S);  // the next iteration prefetches [n0 + 2S, n0 + 3S)
         __syncthreads();
     }
     if (PAIR) {  // last super-step: wait for the peer's samples; nobody leaves while the peer may still store into it
@@ -945,12 +995,13 @@ cudaError_t launch_eq(cudaStream_t st, SigView in, const float *in_peak, float *
 
 cudaError_t launch_compressor(cudaStream_t st, SigView in, const float *in_peak, float *out, int P,
                               int chs, int64_t L, const CompParams *prm, unsigned *out_peak, int *noconv,
-                              int *launches) {
+                              int *ready, int *launches) {
     {
         cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void *>(&compressor_scan_kernel), (int)kCsSmem);
         if (e != cudaSuccess) return e;
     }
-    compressor_scan_kernel<<<P * chs, kCsT, kCsSmem, st>>>(in, in_peak, out, chs, L, prm, out_peak, noconv);
+    static_assert(kCsSB == (1 << kGranuleShift), "the hand-off granule is the compressor super-block");
+    compressor_scan_kernel<<<P * chs, kCsT, kCsSmem, st>>>(in, in_peak, out, chs, L, prm, out_peak, noconv, ready);
     *launches += 1;
     return cudaGetLastError();
 }
@@ -997,9 +1048,19 @@ void reverb_geometry(double sample_rate, ReverbGeom *g) {
     g->block = b;
 }
 
+bool reverb_can_stream(const ReverbGeom &g) {  // the fast path (reverb_core_kernel) is the one that can consume flags
+    int max_comb = 0, max_ap = 0, min_ap = 1 << 30, min_comb = 1 << 30;
+    for (int c = 0; c < 2; ++c) {
+        for (int j = 0; j < 8; ++j) { max_comb = max(max_comb, g.comb_size[c][j]); min_comb = min(min_comb, g.comb_size[c][j]); }
+        for (int j = 0; j < 4; ++j) { max_ap = max(max_ap, g.ap_size[c][j]); min_ap = min(min_ap, g.ap_size[c][j]); }
+    }
+    const int seg = min_comb >= 32 * kRevMaxSegF ? kRevMaxSegF : 32;
+    return g.block >= 32 && min_comb >= 32 * seg && max_comb <= 2 * 32 * seg && max_ap + kRevSub <= kApRing && min_ap >= kRevSub;
+}
+
 cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
                           int stereo, int64_t L, const ReverbGeom &g, const ReverbParams *prm,
-                          unsigned *out_peak, int *launches) {
+                          unsigned *out_peak, const int *ready, int *launches) {
     if (g.block < 32) return cudaErrorInvalidValue;  // sample rate too low for the block scheme
     cudaError_t e;
     // fast path: one CTA per (candidate, channel), L / R CTAs paired in a cluster (reverb_core_kernel)
@@ -1023,7 +1084,8 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
             for (int j = 0; j < 4; ++j) fg.ap_delay[c][j] = g.ap_size[c][j];
         }
         const size_t smem = (size_t)(8 * kCombRing + 4 * kApRing + 10 * kRevMaxS) * sizeof(float) + 16;
-        using Kern = void (*)(SigView, const float *, float *, int, int64_t, ReverbFastGeom, const ReverbParams *, unsigned *);
+        using Kern = void (*)(SigView, const float *, float *, int, int64_t, ReverbFastGeom, const ReverbParams *, unsigned *,
+                              const int *);
         const bool pair = stereo != 0;
         Kern kern = pair ? (seg == kRevMaxSegF ? reverb_core_kernel<kRevMaxSegF, true> : reverb_core_kernel<32, true>)
                          : (seg == kRevMaxSegF ? reverb_core_kernel<kRevMaxSegF, false> : reverb_core_kernel<32, false>);
@@ -1041,11 +1103,12 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kern, in, in_peak, out, chs, L, fg, prm, out_peak);
+        e = cudaLaunchKernelEx(&cfg, kern, in, in_peak, out, chs, L, fg, prm, out_peak, ready);
         if (e != cudaSuccess) return e;
         *launches += 1;
         return cudaGetLastError();
     }
+    if (ready != nullptr) return cudaErrorInvalidValue;  // only the fast path streams (callers check reverb_can_stream)
     const size_t smem = (size_t)(g.total + g.block) * sizeof(float);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (stereo) {

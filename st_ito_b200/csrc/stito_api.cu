@@ -177,7 +177,10 @@ struct stito_handle {
     int n_fft = 2048, hop = 1024, n_mels = 128, embed_dim = 512;
 
     // work buffers
-    DevBuf audio[2], eq_f, eq_s, params, peaks, Wdev, feat, act[3], pooled, emb, fit, flags, xin;
+    DevBuf audio[3], eq_f, eq_s, params, peaks, Wdev, feat, act[3], pooled, emb, fit, flags, xin, ready;
+    // compressor -> reverb streaming (small populations): second stream + fork / join events
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     HostBuf hparams, hW, hflags;
     // flags (device ints): [0], [1] NaN in mid / side embeddings; [2] an activation left the fp16 range of the fp16x3
     // encoder; [3] compressor super-blocks redone serially (Newton iteration did not converge)
@@ -392,13 +395,23 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
     SigView cur = in;
     int cur_chs = chs;
     const float *in_peak = nullptr;
+    // Small populations leave most SMs idle while each of these latency-bound kernels walks its streams one after the
+    // other: a compressor directly followed by the Freeverb then runs as a STREAMING pair -- both kernels resident at the
+    // same time (main + auxiliary stream; 2 * P * chs CTAs must fit the SMs), the reverb consuming super-blocks of 32768
+    // samples as the compressor publishes them (flags in h->ready) -- so the pair costs max(comp, reverb), not the sum.
+    static const bool streaming_on = !(getenv("STITO_DSP_STREAMING") && atoi(getenv("STITO_DSP_STREAMING")) == 0);
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    float *stream_out = nullptr;  // output buffer override for the reverb of a streaming pair
+    const int *stream_ready = nullptr;
     for (int f = 0; f < c.num_fx; ++f) {
         const stito_fx_desc &d = c.fx[f];
         if (d.num_channels == 2 && cur_chs == 1) {  // np.concatenate((x, x)) style_transfer.py:94-95
             cur.stride_c = 0;
             cur_chs = 2;
         }
-        float *out = h->audio[f & 1].as<float>();
+        float *out = stream_out ? stream_out : h->audio[f & 1].as<float>();
+        stream_out = nullptr;
         const bool last = f == c.num_fx - 1;
         unsigned *opk = (last || c.normalize_stages) ? peaks + (size_t)f * P : nullptr;
         const uint8_t *slot = h->params.as<uint8_t>() + (size_t)f * P * kParamSlot;
@@ -411,10 +424,26 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
                              h->eq_f.as<double>(), h->eq_s.as<double>(), opk, launches));
                 break;
             }
-            case STITO_FX_COMPRESSOR:
+            case STITO_FX_COMPRESSOR: {
+                int *ready = nullptr;
+                const bool pair = streaming_on && !c.normalize_stages && f + 1 < c.num_fx && cur_chs == 2 &&
+                                  c.fx[f + 1].kind == STITO_FX_REVERB && c.fx[f + 1].num_channels == 2 &&
+                                  reverb_can_stream(h->rgeom) && 2 * P * cur_chs + 16 <= sm_count;
+                if (pair) {
+                    const size_t nflags = (size_t)P * cur_chs * ((L + kStreamGranule - 1) / kStreamGranule);
+                    CU(h->ready.ensure(nflags * sizeof(int)));
+                    CU(cudaMemsetAsync(h->ready.p, 0, nflags * sizeof(int), st));
+                    CU(h->audio[2].ensure(abytes));
+                    ready = h->ready.as<int>();
+                    stream_ready = ready;
+                    stream_out = h->audio[2].as<float>();  // the reverb must not write where the compressor still reads
+                    CU(cudaEventRecord(h->ev_fork, st));   // everything up to here (EQ output, flags, parameters) ...
+                    CU(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));  // ... precedes the reverb on the second stream
+                }
                 CU(launch_compressor(st, cur, in_peak, out, P, cur_chs, L, reinterpret_cast<const CompParams *>(slot), opk,
-                                     h->flags.as<int>() + 3, launches));
+                                     h->flags.as<int>() + 3, ready, launches));
                 break;
+            }
             case STITO_FX_DISTORTION:
                 CU(launch_distortion(st, cur, in_peak, out, P, cur_chs, L, reinterpret_cast<const DistParams *>(slot), opk, launches));
                 break;
@@ -428,10 +457,16 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
             }
             case STITO_FX_REVERB: {
                 const int stereo = (cur_chs == 2 && d.num_channels == 2) ? 1 : 0;
-                cudaError_t e = launch_reverb(st, cur, in_peak, out, P, cur_chs, stereo, L, h->rgeom,
-                                              reinterpret_cast<const ReverbParams *>(slot), opk, launches);
+                cudaStream_t rst = stream_ready ? h->aux_stream : st;
+                cudaError_t e = launch_reverb(rst, cur, in_peak, out, P, cur_chs, stereo, L, h->rgeom,
+                                              reinterpret_cast<const ReverbParams *>(slot), opk, stream_ready, launches);
                 if (e == cudaErrorInvalidValue) return fail(STITO_EINVAL, "reverb: unsupported sample rate %.1f", c.sample_rate);
                 CU(e);
+                if (stream_ready) {  // join: the main stream continues after the reverb
+                    CU(cudaEventRecord(h->ev_join, h->aux_stream));
+                    CU(cudaStreamWaitEvent(st, h->ev_join, 0));
+                    stream_ready = nullptr;
+                }
                 break;
             }
         }
@@ -537,6 +572,9 @@ int stito_create(const stito_chain_desc *chain, const stito_encoder_weights *wts
                              __FILE__, __LINE__));                                                 \
     } while (0)
     CUB(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < kNumEvents; ++i) CUB(cudaEventCreate(&h->ev[i]));
     for (int i = 0; i < 13; ++i) CUB(cudaEventCreate(&h->ev_conv[i]));
     CUB(h->flags.ensure(kNumFlags * sizeof(int)));
@@ -629,7 +667,10 @@ void stito_destroy(stito_handle *h) {
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     cudaDeviceSynchronize();
     for (void *p : h->owned) cudaFree(p);
-    DevBuf *bufs[] = {&h->input, &h->target, &h->audio[0], &h->audio[1], &h->eq_f, &h->eq_s, &h->params,
+    if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    DevBuf *bufs[] = {&h->input, &h->target, &h->audio[0], &h->audio[1], &h->audio[2], &h->ready, &h->eq_f, &h->eq_s, &h->params,
                       &h->peaks, &h->Wdev, &h->feat, &h->act[0], &h->act[1], &h->act[2], &h->pooled,
                       &h->emb, &h->fit, &h->flags, &h->xin};
     for (DevBuf *b : bufs) b->release();

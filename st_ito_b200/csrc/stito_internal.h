@@ -45,7 +45,7 @@ size_t eq_scratch_doubles(int P, int chs, int64_t L);  // per scratch buffer
 // *noconv (nullable, device) counts super-blocks whose Newton iteration did not converge and were redone serially
 cudaError_t launch_compressor(cudaStream_t st, SigView in, const float *in_peak, float *out, int P,
                               int chs, int64_t L, const CompParams *prm, unsigned *out_peak, int *noconv,
-                              int *launches);
+                              int *ready, int *launches);
 cudaError_t launch_distortion(cudaStream_t st, SigView in, const float *in_peak, float *out, int P,
                               int chs, int64_t L, const DistParams *prm, unsigned *out_peak,
                               int *launches);
@@ -56,7 +56,12 @@ cudaError_t launch_delay(cudaStream_t st, SigView in, const float *in_peak, floa
 // per (candidate, channel).
 cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
                           int stereo, int64_t L, const ReverbGeom &g, const ReverbParams *prm,
-                          unsigned *out_peak, int *launches);
+                          unsigned *out_peak, const int *ready, int *launches);
+// Streaming hand-off compressor -> Freeverb: `ready` = one int per (stream, 32768-sample granule), zeroed before the
+// launch; the compressor sets a flag when that super-block of its output is in memory, the reverb (launched on a second
+// stream, concurrently resident) waits for the flags of the samples it is about to read.
+bool reverb_can_stream(const ReverbGeom &g);
+constexpr int kStreamGranule = 32768;
 cudaError_t launch_copy(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
                         int64_t L, unsigned *out_peak, int *launches);
 // peak[i] = max |x[i, :, :]| as float bits (buffer must be zeroed first).
