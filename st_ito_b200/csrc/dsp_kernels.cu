@@ -929,6 +929,290 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
     }
 }
 
+// ------------------------------------------- reverb, split over a cluster (small populations)
+// With P * chs <= ~40 streams the kernel above leaves three quarters of the GPU idle while every CTA is issue-bound on
+// its 8 comb warps (2.2 us per super-step, 429 super-steps for 10 s).  Here one stereo candidate is a cluster of
+// 2 * NSPLIT CTAs: channel c = rank / NSPLIT, comb group g = rank % NSPLIT.
+//   * every CTA runs CW = 8 / NSPLIT comb filters (one warp each, same arithmetic as above) as a free-running producer;
+//     after super-step k it hands the home CTA of its channel (g == 0) the delayed comb outputs that the all-pass chain
+//     of super-step k + 1 will sum, dly[j][slot][i] = ring_j[n - delay_j], through distributed shared memory, then
+//     arrives (release) on the home CTA's full[slot] mbarrier;
+//   * the home CTA's all-pass group (224 threads) waits (acquire) on full[slot], sums the 8 rows in the ORIGINAL order
+//     (bit-identical to reverb_core_kernel), runs the 4 all-passes, exchanges wet samples with the other channel's home CTA
+//     (same protocol as above) and mixes; when it is done with a slot it arrives on the free[slot] mbarrier of the NSPLIT
+//     producers.  A ring of kRsDepth slots decouples the two sides: there is no CTA-wide barrier in the loop.
+// Per super-step both sides are chain-bound at ~0.8 us instead of issue-bound at 2.2 us.
+constexpr int kRsDepth = 3;
+template <int NSPLIT> struct RsCfg {
+    static constexpr int CW = 8 / NSPLIT;
+    static constexpr int kCombThreads = 32 * CW;
+    static constexpr int kThreads = kCombThreads + kRevSub;
+    static constexpr int kFloats = CW * kCombRing + 8 * kRsDepth * kRevMaxS + 4 * kApRing + 2 * kRevMaxS + 3 * kRevMaxS + 4 * kRevMaxS;
+    static constexpr size_t kSmem = (size_t)kFloats * sizeof(float) + 8 * sizeof(uint64_t) + 16;
+};
+
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    unsigned long long t0 = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok) {  // bounded: a protocol bug must trap, not hang the GPU
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t0 == 0) t0 = t1;
+            if (t1 - t0 > 4000000000ull) {
+                printf("libstito: reverb_split mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+                __trap();
+            }
+        }
+    }
+}
+
+template <int SEG, int NSPLIT>
+__global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kernel(SigView in, float *out, int64_t L,
+                                                                                 ReverbFastGeom g, const ReverbParams *prm,
+                                                                                 unsigned *out_peak, const int *ready) {
+    using Cfg = RsCfg<NSPLIT>;
+    constexpr int CW = Cfg::CW, S = 32 * SEG, RL = 3 * S;
+    constexpr int nsub = (S + kRevSub - 1) / kRevSub;
+    extern __shared__ float sm[];
+    float *ring = sm;                                   // [CW][kCombRing] my comb filters
+    float *dly = ring + CW * kCombRing;                 // [8][kRsDepth][kRevMaxS] delayed comb outputs (home CTA only)
+    float *ap = dly + 8 * kRsDepth * kRevMaxS;          // [4][kApRing]
+    float *inbuf = ap + 4 * kApRing;                    // [2][kRevMaxS] reverb input (l + r) * 0.015 of super-steps k, k + 1
+    float *xraw = inbuf + 2 * kRevMaxS;                 // [3][kRevMaxS] own-channel dry input (home)
+    float *wetb = xraw + 3 * kRevMaxS;                  // [2][2][kRevMaxS] wet: [parity][own, peer]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wetb + 4 * kRevMaxS);  // full[3], free[3], xbar[2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = blockIdx.x % (2 * NSPLIT);
+    const int p = blockIdx.x / (2 * NSPLIT);
+    const int c = rank / NSPLIT, gq = rank % NSPLIT;
+    const bool home = gq == 0;
+    const uint32_t home_rank = (uint32_t)(c * NSPLIT), peer_rank = (uint32_t)((c ^ 1) * NSPLIT);
+    for (int i = tid; i < Cfg::kFloats; i += Cfg::kThreads) sm[i] = 0.0f;
+    const ReverbParams q = prm[p];
+    const int64_t nsteps = (L + S - 1) / S;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    auto map_to = [](uint32_t local, uint32_t target_rank) {
+        uint32_t r;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(target_rank));
+        return r;
+    };
+    if (tid == 0) {
+        for (int s2 = 0; s2 < kRsDepth; ++s2) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(256u));              // full: 8 combs x 32 lanes
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (kRsDepth + s2)), "r"(1u));   // free: the home's all-pass group
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth)), "r"((uint32_t)kRevSub));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + 1)), "r"((uint32_t)kRevSub));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_barrier();  // every CTA of the cluster is resident, zeroed and initialised before anything is stored into it
+
+    const int ngran = (int)((L + (1 << kGranuleShift) - 1) >> kGranuleShift);
+    int64_t avail = ready != nullptr ? 0 : L;
+    auto need_input = [&](int64_t upto) {  // one thread per group; followed by that group's barrier
+        upto = min(upto, L);
+        while (avail < upto) {
+            const int gidx = (int)(avail >> kGranuleShift);
+            await_granule(ready, (p * 2) * ngran + gidx);
+            await_granule(ready, (p * 2 + 1) * ngran + gidx);
+            avail += (1 << kGranuleShift);
+        }
+    };
+    const float *xl = in.base + (int64_t)p * in.stride_p;
+    const float *xr = xl + in.stride_c;
+
+    if (tid < Cfg::kCombThreads) {
+        // ------------------------------------------------------------------ comb group (producer)
+        const int jg = gq * CW + warp;                 // global comb index 0..7 of channel c
+        const int my_delay = g.comb_delay[c][jg];
+        float *my_ring = ring + warp * kCombRing;
+        const float keep = __fsub_rn(1.0f, q.damp);
+        float fstore = 0.0f, dpow = 1.0f;
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) dpow = __fmul_rn(dpow, q.damp);
+        const int i0 = lane * SEG;
+        const uint32_t dly_home = map_to((uint32_t)__cvta_generic_to_shared(dly), home_rank);
+        const uint32_t full_home = map_to(bar0, home_rank);
+        constexpr int kPreC = (2 * kRevMaxS + Cfg::kCombThreads - 1) / Cfg::kCombThreads;  // samples (l and r) per thread
+        // stage the reverb input of one super-step: thread t handles flat indices t, t + T, ... of [S] (l, r summed)
+        constexpr int kPerT = (kRevMaxS + Cfg::kCombThreads - 1) / Cfg::kCombThreads;
+        (void)kPreC;
+        float pl[kPerT], pr[kPerT];
+        auto fetch_in = [&](int64_t base) {
+#pragma unroll
+            for (int k = 0; k < kPerT; ++k) {
+                const int i = tid + k * Cfg::kCombThreads;
+                const int64_t n = base + i;
+                const bool ok = i < S && n < L;
+                pl[k] = ok ? __ldcg(xl + n) : 0.0f;
+                pr[k] = ok ? __ldcg(xr + n) : 0.0f;
+            }
+        };
+        auto park_in = [&](int b) {
+            float *dst = inbuf + b * kRevMaxS;
+#pragma unroll
+            for (int k = 0; k < kPerT; ++k) {
+                const int i = tid + k * Cfg::kCombThreads;
+                if (i < S) dst[i] = __fmul_rn(__fadd_rn(pl[k], pr[k]), 0.015f);
+            }
+        };
+        auto comb_bar = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(Cfg::kCombThreads) : "memory"); };
+        // delayed outputs for the all-pass chain of super-step m -> home CTA's dly[jg][m % depth], then arrive on full
+        auto emit = [&](int64_t m) {
+            const int slot = (int)(m % kRsDepth);
+            if (m >= kRsDepth)  // the home's all-pass group must have finished super-step m - depth (which read this slot)
+                mbar_wait_cluster(bar0 + 8u * (kRsDepth + slot), (uint32_t)(((m / kRsDepth) - 1) & 1));
+            const int wb = (int)(m % 3) * S;
+            int rb = wb - my_delay;
+            if (rb < 0) rb += RL;
+            const float *rp = my_ring + rb + i0;  // contiguous run (continues into the mirror, never wraps)
+            const uint32_t dst = dly_home + (uint32_t)(((jg * kRsDepth + slot) * kRevMaxS + i0) * 4);
+#pragma unroll
+            for (int i = 0; i < SEG; ++i)
+                asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst + 4u * i), "f"(rp[i]) : "memory");
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(full_home + 8u * slot) : "memory");
+        };
+        if (ready != nullptr && tid == 0) need_input(2 * (int64_t)S);
+        if (ready != nullptr) comb_bar();
+        fetch_in(0);
+        park_in(0);
+        comb_bar();
+        emit(0);  // all zeros: nothing has been written to the rings yet
+        int wbase = 0;
+        for (int64_t k = 0; k < nsteps; ++k, wbase = (wbase == 2 * S) ? 0 : wbase + S) {
+            fetch_in((k + 1) * S);  // next super-step's input: the loads fly during this one
+            const float *inb = inbuf + (int)(k & 1) * kRevMaxS;
+            int rb = wbase - my_delay;
+            if (rb < 0) rb += RL;
+            const float *rp = my_ring + rb + i0;
+            float *wp = my_ring + wbase + i0;
+            float o[SEG];
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) o[i] = rp[i];
+            float z = 0.0f;
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) z = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(z, q.damp)));
+            float A = dpow, Bv = z;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float Ap = __shfl_up_sync(0xffffffffu, A, d);
+                const float Bp = __shfl_up_sync(0xffffffffu, Bv, d);
+                if (lane >= d) { Bv = fmaf(Bp, A, Bv); A = A * Ap; }
+            }
+            const float s_out = fmaf(A, fstore, Bv);
+            float sv = __shfl_up_sync(0xffffffffu, s_out, 1);
+            if (lane == 0) sv = fstore;
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) {
+                sv = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(sv, q.damp)));
+                const float tv = undenorm(__fadd_rn(inb[i0 + i], __fmul_rn(sv, q.fb)));
+                wp[i] = tv;
+                if (wbase == 0) wp[RL + i] = tv;  // keep the mirror of the ring head current
+            }
+            fstore = __shfl_sync(0xffffffffu, sv, 31);
+            __syncwarp();
+            if (k + 1 < nsteps) emit(k + 1);
+            park_in((int)((k + 1) & 1));
+            if (ready != nullptr && tid == 0) need_input((k + 3) * (int64_t)S);
+            comb_bar();
+        }
+    } else if (home) {
+        // ------------------------------------------------------------------ all-pass group of the home CTA (consumer)
+        const int a = tid - Cfg::kCombThreads;
+        int ad[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ad[j] = g.ap_delay[c][j];
+        float *dst = out + ((int64_t)p * 2 + c) * L;
+        const float *xc = c ? xr : xl;
+        float pk = 0.0f;
+        const uint32_t peer_wet = map_to((uint32_t)__cvta_generic_to_shared(wetb), peer_rank);
+        const uint32_t peer_xbar = map_to(bar0 + 8u * (2 * kRsDepth), peer_rank);
+        uint32_t free_of[NSPLIT];
+#pragma unroll
+        for (int gg = 0; gg < NSPLIT; ++gg) free_of[gg] = map_to(bar0 + 8u * kRsDepth, home_rank + gg);
+        auto ap_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kRevSub) : "memory"); };
+        constexpr int kPerA = (kRevMaxS + kRevSub - 1) / kRevSub;
+        auto mix = [&](int64_t m) {  // y = wet_own * wet1 + wet_peer * wet2 + x * dry for super-step m
+            const float *wo = wetb + (int)(m & 1) * 2 * kRevMaxS, *wpeer = wo + kRevMaxS, *xr_ = xraw + (int)(m % 3) * kRevMaxS;
+            const int64_t m0 = m * S;
+            const int cnt = (int)min((int64_t)S, L - m0);
+            for (int i = a; i < cnt; i += kRevSub) {
+                const float y = __fadd_rn(__fadd_rn(__fmul_rn(wo[i], q.wet1), __fmul_rn(wpeer[i], q.wet2)), __fmul_rn(xr_[i], q.dry));
+                dst[m0 + i] = y;
+                pk = fmaxf(pk, fabsf(y));
+            }
+        };
+        for (int64_t k = 0; k < nsteps; ++k) {
+            const int64_t n0 = k * S;
+            const int nbase = (int)(n0 & (kApRing * 1024 - 1));
+            const int par = (int)(k & 1), slot = (int)(k % kRsDepth);
+            if (ready != nullptr) {
+                if (a == 0) need_input(n0 + S);
+                ap_bar();
+            }
+            float xd[kPerA];  // own dry samples of this super-step (parked for the mix at the end)
+#pragma unroll
+            for (int t = 0; t < kPerA; ++t) {
+                const int i = a + t * kRevSub;
+                xd[t] = (i < S && n0 + i < L) ? __ldcg(xc + n0 + i) : 0.0f;
+            }
+            if (k > 0) {  // the peer channel's wet samples of the previous super-step have landed -> mix it
+                mbar_wait_cluster(bar0 + 8u * (2 * kRsDepth + (uint32_t)((k - 1) & 1)), (uint32_t)(((k - 1) >> 1) & 1));
+                mix(k - 1);
+            }
+            mbar_wait_cluster(bar0 + 8u * slot, (uint32_t)((k / kRsDepth) & 1));  // the 8 delayed comb rows of this super-step
+            const float *row = dly + slot * kRevMaxS;
+            float *wown = wetb + par * 2 * kRevMaxS;
+            for (int sb = 0; sb < nsub; ++sb) {
+                const int off = sb * kRevSub + a;
+                if (off < S) {
+                    const int n = nbase + off;
+                    float v = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v = __fadd_rn(v, row[j * kRsDepth * kRevMaxS + off]);
+#pragma unroll
+                    for (int s2 = 0; s2 < 4; ++s2) {
+                        const float bv = ap[s2 * kApRing + ((n - ad[s2]) & (kApRing - 1))];
+                        const float tv = undenorm(__fadd_rn(v, __fmul_rn(bv, 0.5f)));
+                        ap[s2 * kApRing + (n & (kApRing - 1))] = tv;
+                        v = __fsub_rn(bv, v);
+                    }
+                    wown[off] = v;
+                    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(peer_wet + (uint32_t)((par * 2 + 1) * kRevMaxS + off) * 4u), "f"(v) : "memory");
+                }
+                if (sb == nsub - 1) {  // park the dry samples before the barrier that ends the super-step
+#pragma unroll
+                    for (int t = 0; t < kPerA; ++t) {
+                        const int i = a + t * kRevSub;
+                        if (i < S) xraw[(int)(k % 3) * kRevMaxS + i] = xd[t];
+                    }
+                }
+                ap_bar();
+            }
+            // my wet samples of this super-step are in the peer's buffer: release them (one arrive per thread)
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_xbar + 8u * (uint32_t)(k & 1)) : "memory");
+            if (a == 0) {  // every all-pass thread has passed the barrier above, i.e. has finished reading dly[.][slot]
+#pragma unroll
+                for (int gg = 0; gg < NSPLIT; ++gg)
+                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_of[gg] + 8u * slot) : "memory");
+            }
+        }
+        if (nsteps > 0) {
+            mbar_wait_cluster(bar0 + 8u * (2 * kRsDepth + (uint32_t)((nsteps - 1) & 1)), (uint32_t)(((nsteps - 1) >> 1) & 1));
+            mix(nsteps - 1);
+        }
+        if (out_peak != nullptr) {
+            pk = warp_max(pk);
+            if (lane == 0) atomic_peak(out_peak, p, pk);
+        }
+    }
+    cluster_barrier();  // nobody leaves while a peer may still store into its shared memory or arrive on its barriers
+}
+
 // ------------------------------------------------------------------- copy / peak
 __global__ void __launch_bounds__(256) copy_kernel(SigView in, const float *in_peak, float *out, int chs,
                                                    int64_t L, unsigned *out_peak) {
@@ -1060,7 +1344,7 @@ bool reverb_can_stream(const ReverbGeom &g) {  // the fast path (reverb_core_ker
 
 cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
                           int stereo, int64_t L, const ReverbGeom &g, const ReverbParams *prm,
-                          unsigned *out_peak, const int *ready, int *launches) {
+                          unsigned *out_peak, const int *ready, int sm_budget, int *launches) {
     if (g.block < 32) return cudaErrorInvalidValue;  // sample rate too low for the block scheme
     cudaError_t e;
     // fast path: one CTA per (candidate, channel), L / R CTAs paired in a cluster (reverb_core_kernel)
@@ -1083,10 +1367,35 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
             for (int j = 0; j < 8; ++j) fg.comb_delay[c][j] = g.comb_size[c][j];
             for (int j = 0; j < 4; ++j) fg.ap_delay[c][j] = g.ap_size[c][j];
         }
+        const bool pair = stereo != 0;
+        // small populations: one candidate = a cluster of 8 CTAs (reverb_split_kernel) when that many SMs are free
+        static const bool split_on = !(getenv("STITO_REVERB_SPLIT") && atoi(getenv("STITO_REVERB_SPLIT")) == 0);
+        if (split_on && pair && in_peak == nullptr && P * 8 <= sm_budget) {
+            using KernS = void (*)(SigView, float *, int64_t, ReverbFastGeom, const ReverbParams *, unsigned *, const int *);
+            KernS ks = seg == kRevMaxSegF ? reverb_split_kernel<kRevMaxSegF, 4> : reverb_split_kernel<32, 4>;
+            const size_t ssm = RsCfg<4>::kSmem;
+            e = ensure_dyn_smem(reinterpret_cast<const void *>(ks), (int)ssm);
+            if (e != cudaSuccess) return e;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(P * 8);
+            cfg.blockDim = dim3(RsCfg<4>::kThreads);
+            cfg.dynamicSmemBytes = ssm;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 8;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, ks, in, out, L, fg, prm, out_peak, ready);
+            if (e != cudaSuccess) return e;
+            *launches += 1;
+            return cudaGetLastError();
+        }
         const size_t smem = (size_t)(8 * kCombRing + 4 * kApRing + 10 * kRevMaxS) * sizeof(float) + 16;
         using Kern = void (*)(SigView, const float *, float *, int, int64_t, ReverbFastGeom, const ReverbParams *, unsigned *,
                               const int *);
-        const bool pair = stereo != 0;
         Kern kern = pair ? (seg == kRevMaxSegF ? reverb_core_kernel<kRevMaxSegF, true> : reverb_core_kernel<32, true>)
                          : (seg == kRevMaxSegF ? reverb_core_kernel<kRevMaxSegF, false> : reverb_core_kernel<32, false>);
         e = ensure_dyn_smem(reinterpret_cast<const void *>(kern), (int)smem);

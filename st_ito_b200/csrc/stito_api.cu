@@ -459,7 +459,8 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
                 const int stereo = (cur_chs == 2 && d.num_channels == 2) ? 1 : 0;
                 cudaStream_t rst = stream_ready ? h->aux_stream : st;
                 cudaError_t e = launch_reverb(rst, cur, in_peak, out, P, cur_chs, stereo, L, h->rgeom,
-                                              reinterpret_cast<const ReverbParams *>(slot), opk, stream_ready, launches);
+                                              reinterpret_cast<const ReverbParams *>(slot), opk, stream_ready,
+                                              sm_count - 4 - (stream_ready ? P * cur_chs : 0), launches);
                 if (e == cudaErrorInvalidValue) return fail(STITO_EINVAL, "reverb: unsupported sample rate %.1f", c.sample_rate);
                 CU(e);
                 if (stream_ready) {  // join: the main stream continues after the reverb

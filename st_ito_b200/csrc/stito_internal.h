@@ -56,7 +56,7 @@ cudaError_t launch_delay(cudaStream_t st, SigView in, const float *in_peak, floa
 // per (candidate, channel).
 cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs,
                           int stereo, int64_t L, const ReverbGeom &g, const ReverbParams *prm,
-                          unsigned *out_peak, const int *ready, int *launches);
+                          unsigned *out_peak, const int *ready, int sm_budget, int *launches);
 // Streaming hand-off compressor -> Freeverb: `ready` = one int per (stream, 32768-sample granule), zeroed before the
 // launch; the compressor sets a flag when that super-block of its output is in memory, the reverb (launched on a second
 // stream, concurrently resident) waits for the flags of the samples it is about to read.
