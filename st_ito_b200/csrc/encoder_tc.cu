@@ -187,6 +187,9 @@ struct ConvTcParams {
     // per-layer shifts from amax and redoes the evaluation after an overflow.
     int *overflow;
     unsigned *amax;
+    // Two-pass variants (per-layer developer knobs STITO_TC_DROP_ALO / STITO_TC_DROP_BLO, bit l = conv layer l): skip the
+    // A_lo * B_hi (activation low parts) or the A_hi * B_lo (weight low parts) correction MMAs of this layer.
+    int drop_alo, drop_blo;
 };
 
 constexpr int kTileM = 128;
@@ -398,13 +401,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                             const uint64_t a_hi = make_sdesc_k<SLABK>(sb + i * 2 * kABytes);
                             const uint64_t a_lo = make_sdesc_k<SLABK>(sb + i * 2 * kABytes + kABytes);
                             // small terms first: they meet the accumulator while it is small
+                            uint32_t acc_on = s > s0 ? 1u : 0u;
+                            if (!p.drop_alo) {
 #pragma unroll
-                            for (int k = 0; k < SLABK / 16; ++k)  // +32 B per K step of 16 inside the swizzle atom
-                                umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, idesc, (s > s0 || k > 0) ? 1u : 0u);
+                                for (int k = 0; k < SLABK / 16; ++k) {  // +32 B per K step of 16 inside the swizzle atom
+                                    umma_f16(d, a_lo + 2 * k, b_hi + 2 * k, idesc, acc_on);
+                                    acc_on = 1u;
+                                }
+                            }
+                            if (!p.drop_blo) {
 #pragma unroll
-                            for (int k = 0; k < SLABK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                                for (int k = 0; k < SLABK / 16; ++k) {
+                                    umma_f16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, acc_on);
+                                    acc_on = 1u;
+                                }
+                            }
 #pragma unroll
-                            for (int k = 0; k < SLABK / 16; ++k) umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                            for (int k = 0; k < SLABK / 16; ++k) {
+                                umma_f16(d, a_hi + 2 * k, b_hi + 2 * k, idesc, acc_on);
+                                acc_on = 1u;
+                            }
                         }
                         umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
                     }
@@ -560,8 +576,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_c64_kernel(const __gr
                         const uint64_t b_cat = make_sdesc(smem_u32(bres + (kh * 3 + kw) * kC64BTap));
 #pragma unroll
                         for (int k = 0; k < kSlabK / 16; ++k) {
-                            umma_f16(d, a_hi + 2 * k, b_cat + 2 * k, idesc_cat, (kh > 0 || k > 0) ? 1u : 0u);
-                            umma_f16(d + BN, a_lo + 2 * k, b_cat + 2 * k, idesc_hi, 1u);
+                            const uint32_t acc_on = (kh > 0 || k > 0) ? 1u : 0u;
+                            // without the weight low parts the first MMA is N = 64 and leaves the correction columns untouched
+                            umma_f16(d, a_hi + 2 * k, b_cat + 2 * k, p.drop_blo ? idesc_hi : idesc_cat, acc_on);
+                            if (!p.drop_alo) umma_f16(d + BN, a_lo + 2 * k, b_cat + 2 * k, idesc_hi, p.drop_blo ? acc_on : 1u);
                         }
                     }
                     umma_commit(&empty[stage]);
@@ -589,9 +607,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_c64_kernel(const __gr
                 tmem_ld32(t0 + BN, u);
                 tmem_ld_wait();
                 const float comp = 1.0f + p.trunc_comp * 12.0f;  // the main columns saw 12 accumulation steps
+                const bool no_corr = p.drop_alo && p.drop_blo;  // nothing was accumulated into the correction columns
 #pragma unroll
                 for (int j = 0; j < kCols; ++j)
-                    acc[j] = __fadd_rn(acc[j], fmaf(__uint_as_float(v[j]), comp, __uint_as_float(u[j])));
+                    acc[j] = __fadd_rn(acc[j], fmaf(__uint_as_float(v[j]), comp, no_corr ? 0.0f : __uint_as_float(u[j])));
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
@@ -1039,6 +1058,11 @@ bool use_wino() {  // STITO_TC_WINOGRAD=0: direct implicit-GEMM convolution on e
     return v != 0;
 }
 
+int drop_mask(const char *name) {  // bit l set: conv layer l (1..11) runs without that correction pass
+    const char *e = getenv(name);
+    return e ? (int)strtol(e, nullptr, 0) : 0;
+}
+
 bool use_c64() {  // STITO_TC_C64=0 falls back to the generic kernel for block 1 (developer knob)
     static int v = -1;
     if (v < 0) { const char *e = getenv("STITO_TC_C64"); v = (e && atoi(e) == 0) ? 0 : 1; }
@@ -1179,6 +1203,8 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, int li,
     p.pool = pool ? 1 : 0;
     p.trunc_comp = chunk_comp();
     p.overflow = ws.overflow_flag;
+    p.drop_alo = (drop_mask("STITO_TC_DROP_ALO") >> li) & 1;
+    p.drop_blo = (drop_mask("STITO_TC_DROP_BLO") >> li) & 1;
     p.out_hi = out_hi; p.out_lo = out_lo; p.out_f32 = out_f32;
     p.N = N; p.H = H; p.W = W; p.Cin = l.cin; p.Cout = l.cout;
     p.BW = W < 64 ? W : 64;
