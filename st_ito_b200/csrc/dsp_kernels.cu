@@ -952,13 +952,13 @@ template <int NSPLIT> struct RsCfg {
 };
 
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
+    uint32_t ok = 0, spins = 0;
     unsigned long long t0 = 0;
     while (!ok) {
         asm volatile("{\n\t.reg .pred p;\n\t"
                      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (!ok) {  // bounded: a protocol bug must trap, not hang the GPU
+        if (!ok && (++spins & 1023u) == 0) {  // bounded: a protocol bug must trap, not hang the GPU
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             if (t0 == 0) t0 = t1;
@@ -1002,7 +1002,7 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
     };
     if (tid == 0) {
         for (int s2 = 0; s2 < kRsDepth; ++s2) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(256u));              // full: 8 combs x 32 lanes
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(8u));                // full: one arrive per comb warp
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (kRsDepth + s2)), "r"(1u));   // free: the home's all-pass group
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth)), "r"((uint32_t)kRevSub));
@@ -1069,12 +1069,24 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
             const int wb = (int)(m % 3) * S;
             int rb = wb - my_delay;
             if (rb < 0) rb += RL;
-            const float *rp = my_ring + rb + i0;  // contiguous run (continues into the mirror, never wraps)
-            const uint32_t dst = dly_home + (uint32_t)(((jg * kRsDepth + slot) * kRevMaxS + i0) * 4);
+            // the S delayed samples are one contiguous run of my ring (it continues into the mirror, never wraps); the warp
+            // copies it as 16-byte distributed-shared-memory stores (scalar stores -- 35 per lane -- made the remote store
+            // path the bottleneck of the whole kernel), then ONE lane arrives: __syncwarp orders the other lanes' stores
+            // before its release
+            const float *rp = my_ring + rb;
+            const uint32_t dst = dly_home + (uint32_t)((jg * kRsDepth + slot) * kRevMaxS) * 4u;
 #pragma unroll
-            for (int i = 0; i < SEG; ++i)
-                asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst + 4u * i), "f"(rp[i]) : "memory");
-            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(full_home + 8u * slot) : "memory");
+            for (int t = 0; t < (S / 4 + 31) / 32; ++t) {
+                const int v4 = lane + 32 * t;
+                if (v4 < S / 4) {
+                    const float *src = rp + 4 * v4;
+                    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * v4), "f"(src[0]), "f"(src[1]),
+                                 "f"(src[2]), "f"(src[3]) : "memory");
+                }
+            }
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(full_home + 8u * slot) : "memory");
         };
         if (ready != nullptr && tid == 0) need_input(2 * (int64_t)S);
         if (ready != nullptr) comb_bar();
