@@ -947,7 +947,8 @@ template <int NSPLIT> struct RsCfg {
     static constexpr int CW = 8 / NSPLIT;
     static constexpr int kCombThreads = 32 * CW;
     static constexpr int kThreads = kCombThreads + kRevSub;
-    static constexpr int kFloats = CW * kCombRing + 8 * kRsDepth * kRevMaxS + 4 * kApRing + 2 * kRevMaxS + 3 * kRevMaxS + 4 * kRevMaxS;
+    static constexpr int kFloats = CW * kCombRing + 8 * kRsDepth * kRevMaxS + 4 * kApRing + 2 * kRevMaxS + 3 * kRevMaxS + 4 * kRevMaxS +
+                                   CW * kRsDepth * kRevMaxS;  // last term: staging of the delayed rows (source of the bulk copies)
     static constexpr size_t kSmem = (size_t)kFloats * sizeof(float) + 8 * sizeof(uint64_t) + 16;
 };
 
@@ -984,7 +985,8 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
     float *inbuf = ap + 4 * kApRing;                    // [2][kRevMaxS] reverb input (l + r) * 0.015 of super-steps k, k + 1
     float *xraw = inbuf + 2 * kRevMaxS;                 // [3][kRevMaxS] own-channel dry input (home)
     float *wetb = xraw + 3 * kRevMaxS;                  // [2][2][kRevMaxS] wet: [parity][own, peer]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(wetb + 4 * kRevMaxS);  // full[3], free[3], xbar[2]
+    float *stage = wetb + 4 * kRevMaxS;                 // [CW][kRsDepth][kRevMaxS] delayed rows staged for the bulk copy
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + CW * kRsDepth * kRevMaxS);  // full[3], free[3], xbar[2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = blockIdx.x % (2 * NSPLIT);
     const int p = blockIdx.x / (2 * NSPLIT);
@@ -1002,11 +1004,14 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
     };
     if (tid == 0) {
         for (int s2 = 0; s2 < kRsDepth; ++s2) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(8u));                // full: one arrive per comb warp
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(1u));                // full: armed with 8 rows of bytes
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (kRsDepth + s2)), "r"(1u));   // free: the home's all-pass group
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth)), "r"((uint32_t)kRevSub));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + 1)), "r"((uint32_t)kRevSub));
+        if (home)  // arm the first phase of every slot: 8 delayed rows of S floats will land by bulk copy
+            for (int s2 = 0; s2 < kRsDepth; ++s2)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s2), "r"((uint32_t)(8 * S * 4)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_barrier();  // every CTA of the cluster is resident, zeroed and initialised before anything is stored into it
@@ -1069,24 +1074,30 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
             const int wb = (int)(m % 3) * S;
             int rb = wb - my_delay;
             if (rb < 0) rb += RL;
-            // the S delayed samples are one contiguous run of my ring (it continues into the mirror, never wraps); the warp
-            // copies it as 16-byte distributed-shared-memory stores (scalar stores -- 35 per lane -- made the remote store
-            // path the bottleneck of the whole kernel), then ONE lane arrives: __syncwarp orders the other lanes' stores
-            // before its release
+            // The S delayed samples are one contiguous run of my ring (it continues into the mirror, never wraps).  The warp
+            // copies it into a 16-byte aligned staging row and ONE lane hands it to the bulk-copy engine, which writes the
+            // home CTA's dly row through distributed shared memory and completes the transaction on the home's full[slot]
+            // mbarrier -- no remote stores and no release fence on the comb filters' critical path (they cost ~1 us per
+            // super-step: ncu source view of the first version, profiles/r02d_*).  The staging row is reused for super-step
+            // m + depth, i.e. only after free[slot] said that the all-pass group has consumed this one.
             const float *rp = my_ring + rb;
-            const uint32_t dst = dly_home + (uint32_t)((jg * kRsDepth + slot) * kRevMaxS) * 4u;
+            float *srow = stage + (warp * kRsDepth + slot) * kRevMaxS;
 #pragma unroll
             for (int t = 0; t < (S / 4 + 31) / 32; ++t) {
                 const int v4 = lane + 32 * t;
                 if (v4 < S / 4) {
                     const float *src = rp + 4 * v4;
-                    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * v4), "f"(src[0]), "f"(src[1]),
-                                 "f"(src[2]), "f"(src[3]) : "memory");
+                    *reinterpret_cast<float4 *>(srow + 4 * v4) = make_float4(src[0], src[1], src[2], src[3]);
                 }
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my staging writes -> visible to the async proxy
             __syncwarp();
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(full_home + 8u * slot) : "memory");
+            if (lane == 0) {
+                const uint32_t dst = dly_home + (uint32_t)((jg * kRsDepth + slot) * kRevMaxS) * 4u;
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "r"((uint32_t)__cvta_generic_to_shared(srow)), "r"((uint32_t)(S * 4)), "r"(full_home + 8u * slot)
+                             : "memory");
+            }
         };
         if (ready != nullptr && tid == 0) need_input(2 * (int64_t)S);
         if (ready != nullptr) comb_bar();
@@ -1208,6 +1219,8 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
             // my wet samples of this super-step are in the peer's buffer: release them (one arrive per thread)
             asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_xbar + 8u * (uint32_t)(k & 1)) : "memory");
             if (a == 0) {  // every all-pass thread has passed the barrier above, i.e. has finished reading dly[.][slot]
+                // arm the slot's next phase, then tell the NSPLIT producers that the slot (and their staging row) is free
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"((uint32_t)(8 * S * 4)) : "memory");
 #pragma unroll
                 for (int gg = 0; gg < NSPLIT; ++gg)
                     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_of[gg] + 8u * slot) : "memory");
