@@ -183,6 +183,7 @@ STITO_API int stito_cma_create(const double *x0, int D, double sigma0, int popsi
 STITO_API void stito_cma_destroy(stito_cma *es);
 STITO_API int stito_cma_eig(const double *A, int n, double *V, double *d); /* symmetric eigensolver of the update (tests) */
 STITO_API int stito_cma_ask(stito_cma *es, double *X);
+STITO_API int stito_cma_geno(const stito_cma *es, double *G); /* search points of the last ask before the box map (tests) */
 STITO_API int stito_cma_tell(stito_cma *es, const double *X, const double *f);
 STITO_API int stito_cma_result(const stito_cma *es, double *xbest, double *fbest, int *has_best, double *xfavorite,
                                double *sigma, double *stds, int64_t *evals_best, int64_t *evaluations,

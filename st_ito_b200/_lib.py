@@ -98,6 +98,7 @@ EXPORTS = {
     "stito_cma_destroy": (None, [c_void_p]),
     "stito_cma_eig": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "stito_cma_ask": (c_int, [c_void_p, c_void_p]),
+    "stito_cma_geno": (c_int, [c_void_p, c_void_p]),
     "stito_cma_tell": (c_int, [c_void_p, c_void_p, c_void_p]),
     "stito_cma_result": (c_int, [c_void_p] + [c_void_p] * 11),
     "stito_last_error": (c_char_p, []),

@@ -324,6 +324,13 @@ int stito_cma_ask(stito_cma *es, double *X) {
     return STITO_OK;
 }
 
+/* genotypes (pre-box-transform search points) of the last ask, [popsize][D] (tests: the update is a function of these) */
+int stito_cma_geno(const stito_cma *es, double *G) {
+    if (!es || !G) return STITO_EINVAL;
+    std::memcpy(G, es->geno.data(), es->geno.size() * sizeof(double));
+    return STITO_OK;
+}
+
 /* X: the solutions handed out by the preceding ask (only the best one is kept), f [popsize] */
 int stito_cma_tell(stito_cma *es, const double *X, const double *fin) {
     if (!es || !X || !fin) return STITO_EINVAL;

@@ -300,3 +300,64 @@ def test_load_param_model_reads_a_lightning_checkpoint(tmp_path):
     assert got["logmel_extractor.melW"].shape == (1025, 128)
     with pytest.raises(FileNotFoundError, match="afx-rep.ckpt"):
         load_param_model(str(tmp_path / "missing" / "afx-rep.ckpt"))
+
+
+# ------------------------------------------------------------------------- native CMA-ES (C ABI, host only)
+def test_native_cma_matches_the_numpy_statement_of_the_algorithm():
+    """stito_cma_* (cma_host.cpp) against st_ito_b200.cma.PyCMAEvolutionStrategy: same update equations, so feeding both
+    the SAME populations and fitness values must give the same mean / sigma / covariance scale; the eigensolver is
+    checked against numpy; ask() is feasible, deterministic per seed and different across seeds."""
+    import ctypes
+
+    from st_ito_b200 import _lib, cma
+
+    L = _lib.lib()
+    rng = np.random.RandomState(0)
+    for n in (1, 2, 7, 29, 50):
+        M = rng.randn(n, n)
+        A = M @ M.T + 0.1 * np.eye(n)
+        V, d = np.empty((n, n)), np.empty(n)
+        assert L.stito_cma_eig(A.ctypes.data, n, V.ctypes.data, d.ctypes.data) == 0
+        assert np.abs((V * d) @ V.T - A).max() <= 1e-12 * np.abs(A).max()
+        assert np.abs(V.T @ V - np.eye(n)).max() <= 1e-12
+        assert np.allclose(np.sort(d), np.linalg.eigvalsh(A), rtol=1e-10, atol=1e-12)
+
+    target = np.linspace(0.1, 0.9, 12)
+    f = lambda x: float(np.sum((x - target) ** 2))
+    opts = {"bounds": [0, 1], "popsize": 16, "seed": 5, "verbose": -9}
+    nat = cma.CMAEvolutionStrategy(np.full(12, 0.5), 0.33, dict(opts))
+    assert isinstance(nat, cma.NativeCMAEvolutionStrategy) and nat.result[0] is None
+    py = cma.CMAEvolutionStrategy(np.full(12, 0.5), 0.33, dict(opts, implementation="numpy"))
+    assert isinstance(py, cma.PyCMAEvolutionStrategy)
+    for it in range(40):
+        X = nat.ask()
+        assert len(X) == 16 and all(np.all((x >= 0) & (x <= 1)) for x in X)
+        fv = [f(x) for x in X]
+        # drive the numpy implementation with the native one's genotypes: replace its sample, keep its update
+        py.ask()
+        py._geno = np.ascontiguousarray(_native_geno(nat, L))
+        nat.tell(X, fv)
+        py.tell(X, fv)
+        assert np.allclose(py.result.xfavorite, nat.result.xfavorite, rtol=1e-9, atol=1e-12), it
+        assert abs(py.sigma - nat.sigma) <= 1e-9 * py.sigma
+        assert np.allclose(py.result.stds, nat.result.stds, rtol=1e-8)
+    assert nat.result[1] == py.result[1] and np.array_equal(nat.result[0], py.result[0])
+    # optimisation quality + determinism
+    runs = []
+    for seed in (5, 5, 6):
+        es = cma.CMAEvolutionStrategy(np.full(12, 0.5), 0.33, dict(opts, seed=seed))
+        for _ in range(120):
+            X = es.ask()
+            es.tell(X, [f(x) for x in X])
+        runs.append((es.result[0].copy(), es.result[1]))
+    assert runs[0][1] < 1e-6 and np.allclose(runs[0][0], target, atol=2e-3)
+    assert np.array_equal(runs[0][0], runs[1][0]) and not np.array_equal(runs[0][0], runs[2][0])
+    with pytest.raises(ValueError):
+        nat.tell(X, fv)  # no preceding ask()
+
+
+def _native_geno(es, L):
+    """Search points (before the box map) of the native strategy's last ask(): stito_cma_geno."""
+    G = np.empty((es.popsize, es.N))
+    assert L.stito_cma_geno(es._h, G.ctypes.data) == 0
+    return G
