@@ -1007,11 +1007,14 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(1u));                // full: armed with 8 rows of bytes
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (kRsDepth + s2)), "r"(1u));   // free: the home's all-pass group
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth)), "r"((uint32_t)kRevSub));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + 1)), "r"((uint32_t)kRevSub));
-        if (home)  // arm the first phase of every slot: 8 delayed rows of S floats will land by bulk copy
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth)), "r"(1u));       // xbar: armed with one
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + 1)), "r"(1u));   // wet row of bytes
+        if (home) {  // arm the first phases: 8 delayed rows of S floats per slot, one wet row of the peer channel per parity
             for (int s2 = 0; s2 < kRsDepth; ++s2)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s2), "r"((uint32_t)(8 * S * 4)) : "memory");
+            for (int s2 = 0; s2 < 2; ++s2)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + s2)), "r"((uint32_t)(S * 4)) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_barrier();  // every CTA of the cluster is resident, zeroed and initialised before anything is stored into it
@@ -1184,7 +1187,10 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
                 xd[t] = (i < S && n0 + i < L) ? __ldcg(xc + n0 + i) : 0.0f;
             }
             if (k > 0) {  // the peer channel's wet samples of the previous super-step have landed -> mix it
-                mbar_wait_cluster(bar0 + 8u * (2 * kRsDepth + (uint32_t)((k - 1) & 1)), (uint32_t)(((k - 1) >> 1) & 1));
+                const uint32_t xb = bar0 + 8u * (2 * kRsDepth + (uint32_t)((k - 1) & 1));
+                mbar_wait_cluster(xb, (uint32_t)(((k - 1) >> 1) & 1));
+                // re-arm this parity for the peer's super-step k + 1 (it cannot send that before it has my super-step k)
+                if (a == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xb), "r"((uint32_t)(S * 4)) : "memory");
                 mix(k - 1);
             }
             mbar_wait_cluster(bar0 + 8u * slot, (uint32_t)((k / kRsDepth) & 1));  // the 8 delayed comb rows of this super-step
@@ -1205,7 +1211,6 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
                         v = __fsub_rn(bv, v);
                     }
                     wown[off] = v;
-                    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(peer_wet + (uint32_t)((par * 2 + 1) * kRevMaxS + off) * 4u), "f"(v) : "memory");
                 }
                 if (sb == nsub - 1) {  // park the dry samples before the barrier that ends the super-step
 #pragma unroll
@@ -1213,18 +1218,24 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
                         const int i = a + t * kRevSub;
                         if (i < S) xraw[(int)(k % 3) * kRevMaxS + i] = xd[t];
                     }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my wet samples -> visible to the bulk copy below
                 }
                 ap_bar();
             }
-            // my wet samples of this super-step are in the peer's buffer: release them (one arrive per thread)
-            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_xbar + 8u * (uint32_t)(k & 1)) : "memory");
-            if (a == 0) {  // every all-pass thread has passed the barrier above, i.e. has finished reading dly[.][slot]
-                // arm the slot's next phase, then tell the NSPLIT producers that the slot (and their staging row) is free
+            // Every all-pass thread has passed the barrier above: the wet row of this super-step is complete and dly[.][slot]
+            // has been read.  ONE thread ships the wet row to the peer channel's home CTA (bulk copy through distributed shared
+            // memory, completing on the peer's xbar) -- the first version stored every sample remotely and had all 224 threads
+            // release-arrive on the peer, ~1 us of fence stalls per super-step -- and re-arms the slot; NSPLIT threads tell one
+            // producer CTA each that the slot (and its staging row) is free.
+            if (a == 0) {
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(peer_wet + (uint32_t)((par * 2 + 1) * kRevMaxS) * 4u), "r"((uint32_t)__cvta_generic_to_shared(wown)),
+                               "r"((uint32_t)(S * 4)), "r"(peer_xbar + 8u * (uint32_t)(k & 1)) : "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"((uint32_t)(8 * S * 4)) : "memory");
-#pragma unroll
-                for (int gg = 0; gg < NSPLIT; ++gg)
-                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_of[gg] + 8u * slot) : "memory");
             }
+            __syncwarp();
+            if (a < NSPLIT)
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_of[a] + 8u * slot) : "memory");
         }
         if (nsteps > 0) {
             mbar_wait_cluster(bar0 + 8u * (2 * kRsDepth + (uint32_t)((nsteps - 1) & 1)), (uint32_t)(((nsteps - 1) >> 1) & 1));
