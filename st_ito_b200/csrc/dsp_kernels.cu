@@ -947,9 +947,9 @@ template <int NSPLIT> struct RsCfg {
     static constexpr int CW = 8 / NSPLIT;
     static constexpr int kCombThreads = 32 * CW;
     static constexpr int kThreads = kCombThreads + kRevSub;
-    static constexpr int kFloats = CW * kCombRing + 8 * kRsDepth * kRevMaxS + 4 * kApRing + 2 * kRevMaxS + 3 * kRevMaxS + 4 * kRevMaxS +
+    static constexpr int kFloats = CW * kCombRing + 8 * kRsDepth * kRevMaxS + 4 * kApRing + 2 * kRevMaxS + 6 * kRevMaxS +
                                    CW * kRsDepth * kRevMaxS;  // last term: staging of the delayed rows (source of the bulk copies)
-    static constexpr size_t kSmem = (size_t)kFloats * sizeof(float) + 8 * sizeof(uint64_t) + 16;
+    static constexpr size_t kSmem = (size_t)kFloats * sizeof(float) + 9 * sizeof(uint64_t) + 16;
 };
 
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -983,10 +983,9 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
     float *dly = ring + CW * kCombRing;                 // [8][kRsDepth][kRevMaxS] delayed comb outputs (home CTA only)
     float *ap = dly + 8 * kRsDepth * kRevMaxS;          // [4][kApRing]
     float *inbuf = ap + 4 * kApRing;                    // [2][kRevMaxS] reverb input (l + r) * 0.015 of super-steps k, k + 1
-    float *xraw = inbuf + 2 * kRevMaxS;                 // [3][kRevMaxS] own-channel dry input (home)
-    float *wetb = xraw + 3 * kRevMaxS;                  // [2][2][kRevMaxS] wet: [parity][own, peer]
-    float *stage = wetb + 4 * kRevMaxS;                 // [CW][kRsDepth][kRevMaxS] delayed rows staged for the bulk copy
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + CW * kRsDepth * kRevMaxS);  // full[3], free[3], xbar[2]
+    float *wetb = inbuf + 2 * kRevMaxS;                 // [3][2][kRevMaxS] wet rows of super-steps k, k - 1, k - 2: [k % 3][own, peer]
+    float *stage = wetb + 6 * kRevMaxS;                 // [CW][kRsDepth][kRevMaxS] delayed rows staged for the bulk copy
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + CW * kRsDepth * kRevMaxS);  // full[3], free[3], xbar[3]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = blockIdx.x % (2 * NSPLIT);
     const int p = blockIdx.x / (2 * NSPLIT);
@@ -1007,12 +1006,12 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(1u));                // full: armed with 8 rows of bytes
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (kRsDepth + s2)), "r"(1u));   // free: the home's all-pass group
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth)), "r"(1u));       // xbar: armed with one
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + 1)), "r"(1u));   // wet row of bytes
+        for (int s2 = 0; s2 < 3; ++s2)  // xbar: armed with one wet row of bytes
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + s2)), "r"(1u));
         if (home) {  // arm the first phases: 8 delayed rows of S floats per slot, one wet row of the peer channel per parity
             for (int s2 = 0; s2 < kRsDepth; ++s2)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s2), "r"((uint32_t)(8 * S * 4)) : "memory");
-            for (int s2 = 0; s2 < 2; ++s2)
+            for (int s2 = 0; s2 < 3; ++s2)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + s2)), "r"((uint32_t)(S * 4)) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1161,41 +1160,43 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
 #pragma unroll
         for (int gg = 0; gg < NSPLIT; ++gg) free_of[gg] = map_to(bar0 + 8u * kRsDepth, home_rank + gg);
         auto ap_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kRevSub) : "memory"); };
-        constexpr int kPerA = (kRevMaxS + kRevSub - 1) / kRevSub;
-        auto mix = [&](int64_t m) {  // y = wet_own * wet1 + wet_peer * wet2 + x * dry for super-step m
-            const float *wo = wetb + (int)(m & 1) * 2 * kRevMaxS, *wpeer = wo + kRevMaxS, *xr_ = xraw + (int)(m % 3) * kRevMaxS;
+        auto xbar_of = [&](int64_t m) { return bar0 + 8u * (2 * kRsDepth + (uint32_t)(m % 3)); };
+        auto xpar_of = [&](int64_t m) { return (uint32_t)((m / 3) & 1); };
+        // y = wet_own * wet1 + wet_peer * wet2 + x * dry for super-step m (the dry samples are re-read from global memory:
+        // L2 hits, and it frees the shared memory the third wet row needs)
+        auto mix = [&](int64_t m) {
+            const float *wo = wetb + (int)(m % 3) * 2 * kRevMaxS, *wpeer = wo + kRevMaxS;
             const int64_t m0 = m * S;
             const int cnt = (int)min((int64_t)S, L - m0);
             for (int i = a; i < cnt; i += kRevSub) {
-                const float y = __fadd_rn(__fadd_rn(__fmul_rn(wo[i], q.wet1), __fmul_rn(wpeer[i], q.wet2)), __fmul_rn(xr_[i], q.dry));
+                const float x = __ldcg(xc + m0 + i);
+                const float y = __fadd_rn(__fadd_rn(__fmul_rn(wo[i], q.wet1), __fmul_rn(wpeer[i], q.wet2)), __fmul_rn(x, q.dry));
                 dst[m0 + i] = y;
                 pk = fmaxf(pk, fabsf(y));
             }
         };
+        // The wet exchange with the other channel is kept OFF the critical loop: super-step m is mixed two super-steps
+        // later (its peer row has long landed), and the only wait for the peer -- "your super-step k - 1 row has arrived",
+        // which also proves that the peer has mixed k - 3 and so freed the row this step's copy will overwrite -- sits at
+        // the END of super-step k, one compute phase after the peer sent it.  (Waiting for row k - 1 at the START of
+        // super-step k put a DSMEM round trip into every iteration: 2.3 us per super-step instead of < 1.)
         for (int64_t k = 0; k < nsteps; ++k) {
             const int64_t n0 = k * S;
             const int nbase = (int)(n0 & (kApRing * 1024 - 1));
-            const int par = (int)(k & 1), slot = (int)(k % kRsDepth);
-            if (ready != nullptr) {
-                if (a == 0) need_input(n0 + S);
+            const int slot = (int)(k % kRsDepth);
+            if (ready != nullptr) {  // mix(k - 2) reads the dry input up to (k - 1) S: covered by what the combs needed long ago;
+                if (a == 0) need_input(n0);  // kept for the first steps / degenerate lengths
                 ap_bar();
             }
-            float xd[kPerA];  // own dry samples of this super-step (parked for the mix at the end)
-#pragma unroll
-            for (int t = 0; t < kPerA; ++t) {
-                const int i = a + t * kRevSub;
-                xd[t] = (i < S && n0 + i < L) ? __ldcg(xc + n0 + i) : 0.0f;
-            }
-            if (k > 0) {  // the peer channel's wet samples of the previous super-step have landed -> mix it
-                const uint32_t xb = bar0 + 8u * (2 * kRsDepth + (uint32_t)((k - 1) & 1));
-                mbar_wait_cluster(xb, (uint32_t)(((k - 1) >> 1) & 1));
-                // re-arm this parity for the peer's super-step k + 1 (it cannot send that before it has my super-step k)
-                if (a == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xb), "r"((uint32_t)(S * 4)) : "memory");
-                mix(k - 1);
+            if (k >= 2) {
+                mbar_wait_cluster(xbar_of(k - 2), xpar_of(k - 2));  // complete since the end of super-step k - 1: acquire only
+                if (a == 0)  // re-arm this barrier for the peer's super-step k + 1
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xbar_of(k - 2)), "r"((uint32_t)(S * 4)) : "memory");
+                mix(k - 2);
             }
             mbar_wait_cluster(bar0 + 8u * slot, (uint32_t)((k / kRsDepth) & 1));  // the 8 delayed comb rows of this super-step
             const float *row = dly + slot * kRevMaxS;
-            float *wown = wetb + par * 2 * kRevMaxS;
+            float *wown = wetb + (int)(k % 3) * 2 * kRevMaxS;
             for (int sb = 0; sb < nsub; ++sb) {
                 const int off = sb * kRevSub + a;
                 if (off < S) {
@@ -1212,34 +1213,27 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
                     }
                     wown[off] = v;
                 }
-                if (sb == nsub - 1) {  // park the dry samples before the barrier that ends the super-step
-#pragma unroll
-                    for (int t = 0; t < kPerA; ++t) {
-                        const int i = a + t * kRevSub;
-                        if (i < S) xraw[(int)(k % 3) * kRevMaxS + i] = xd[t];
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my wet samples -> visible to the bulk copy below
-                }
+                if (sb == nsub - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // wet samples -> visible to the bulk copy
                 ap_bar();
             }
             // Every all-pass thread has passed the barrier above: the wet row of this super-step is complete and dly[.][slot]
             // has been read.  ONE thread ships the wet row to the peer channel's home CTA (bulk copy through distributed shared
-            // memory, completing on the peer's xbar) -- the first version stored every sample remotely and had all 224 threads
-            // release-arrive on the peer, ~1 us of fence stalls per super-step -- and re-arms the slot; NSPLIT threads tell one
-            // producer CTA each that the slot (and its staging row) is free.
+            // memory, completing on the peer's xbar) and re-arms the slot; NSPLIT threads tell one producer CTA each that the
+            // slot (and its staging row) is free.
             if (a == 0) {
+                if (k >= 1) mbar_wait_cluster(xbar_of(k - 1), xpar_of(k - 1));  // peer is past k - 1 => it has mixed k - 3: row free
                 asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(peer_wet + (uint32_t)((par * 2 + 1) * kRevMaxS) * 4u), "r"((uint32_t)__cvta_generic_to_shared(wown)),
-                               "r"((uint32_t)(S * 4)), "r"(peer_xbar + 8u * (uint32_t)(k & 1)) : "memory");
+                             ::"r"(peer_wet + (uint32_t)(((int)(k % 3) * 2 + 1) * kRevMaxS) * 4u), "r"((uint32_t)__cvta_generic_to_shared(wown)),
+                               "r"((uint32_t)(S * 4)), "r"(peer_xbar + 8u * (uint32_t)(k % 3)) : "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"((uint32_t)(8 * S * 4)) : "memory");
             }
             __syncwarp();
             if (a < NSPLIT)
                 asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_of[a] + 8u * slot) : "memory");
         }
-        if (nsteps > 0) {
-            mbar_wait_cluster(bar0 + 8u * (2 * kRsDepth + (uint32_t)((nsteps - 1) & 1)), (uint32_t)(((nsteps - 1) >> 1) & 1));
-            mix(nsteps - 1);
+        for (int64_t m = max((int64_t)0, nsteps - 2); m < nsteps; ++m) {  // the last two super-steps are still unmixed
+            mbar_wait_cluster(xbar_of(m), xpar_of(m));
+            mix(m);
         }
         if (out_peak != nullptr) {
             pk = warp_max(pk);
