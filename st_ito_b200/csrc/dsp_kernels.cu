@@ -1164,15 +1164,27 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
         auto xpar_of = [&](int64_t m) { return (uint32_t)((m / 3) & 1); };
         // y = wet_own * wet1 + wet_peer * wet2 + x * dry for super-step m (the dry samples are re-read from global memory:
         // L2 hits, and it frees the shared memory the third wet row needs)
-        auto mix = [&](int64_t m) {
+        constexpr int kPerA = (kRevMaxS + kRevSub - 1) / kRevSub;
+        auto load_dry = [&](int64_t m, float (&xd)[kPerA]) {  // issued a compute phase before mix(m) consumes them
+            const int64_t m0 = m * S;
+#pragma unroll
+            for (int t = 0; t < kPerA; ++t) {
+                const int i = a + t * kRevSub;
+                xd[t] = (i < S && m0 + i < L) ? __ldcg(xc + m0 + i) : 0.0f;
+            }
+        };
+        auto mix = [&](int64_t m, const float (&xd)[kPerA]) {
             const float *wo = wetb + (int)(m % 3) * 2 * kRevMaxS, *wpeer = wo + kRevMaxS;
             const int64_t m0 = m * S;
             const int cnt = (int)min((int64_t)S, L - m0);
-            for (int i = a; i < cnt; i += kRevSub) {
-                const float x = __ldcg(xc + m0 + i);
-                const float y = __fadd_rn(__fadd_rn(__fmul_rn(wo[i], q.wet1), __fmul_rn(wpeer[i], q.wet2)), __fmul_rn(x, q.dry));
-                dst[m0 + i] = y;
-                pk = fmaxf(pk, fabsf(y));
+#pragma unroll
+            for (int t = 0; t < kPerA; ++t) {
+                const int i = a + t * kRevSub;
+                if (i < cnt) {
+                    const float y = __fadd_rn(__fadd_rn(__fmul_rn(wo[i], q.wet1), __fmul_rn(wpeer[i], q.wet2)), __fmul_rn(xd[t], q.dry));
+                    dst[m0 + i] = y;
+                    pk = fmaxf(pk, fabsf(y));
+                }
             }
         };
         // The wet exchange with the other channel is kept OFF the critical loop: super-step m is mixed two super-steps
@@ -1188,12 +1200,8 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
                 if (a == 0) need_input(n0);  // kept for the first steps / degenerate lengths
                 ap_bar();
             }
-            if (k >= 2) {
-                mbar_wait_cluster(xbar_of(k - 2), xpar_of(k - 2));  // complete since the end of super-step k - 1: acquire only
-                if (a == 0)  // re-arm this barrier for the peer's super-step k + 1
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xbar_of(k - 2)), "r"((uint32_t)(S * 4)) : "memory");
-                mix(k - 2);
-            }
+            float xd[kPerA];
+            if (k >= 2) load_dry(k - 2, xd);  // dry samples of the super-step mixed at the end of this one: in flight during the all-passes
             mbar_wait_cluster(bar0 + 8u * slot, (uint32_t)((k / kRsDepth) & 1));  // the 8 delayed comb rows of this super-step
             const float *row = dly + slot * kRevMaxS;
             float *wown = wetb + (int)(k % 3) * 2 * kRevMaxS;
@@ -1213,8 +1221,16 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
                     }
                     wown[off] = v;
                 }
-                if (sb == nsub - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // wet samples -> visible to the bulk copy
-                ap_bar();
+                if (sb == nsub - 1) {
+                    if (k >= 2) {  // mix super-step k - 2: its peer row landed a whole super-step ago (acquire only)
+                        mbar_wait_cluster(xbar_of(k - 2), xpar_of(k - 2));
+                        if (a == 0)  // re-arm this barrier for the peer's super-step k + 1
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xbar_of(k - 2)), "r"((uint32_t)(S * 4)) : "memory");
+                        mix(k - 2, xd);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // wet samples -> visible to the bulk copy
+                }
+                ap_bar();  // after the last sub-block: everybody has also finished reading the rows mix(k - 2) used
             }
             // Every all-pass thread has passed the barrier above: the wet row of this super-step is complete and dly[.][slot]
             // has been read.  ONE thread ships the wet row to the peer channel's home CTA (bulk copy through distributed shared
@@ -1232,8 +1248,10 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
                 asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_of[a] + 8u * slot) : "memory");
         }
         for (int64_t m = max((int64_t)0, nsteps - 2); m < nsteps; ++m) {  // the last two super-steps are still unmixed
+            float xd[kPerA];
+            load_dry(m, xd);
             mbar_wait_cluster(xbar_of(m), xpar_of(m));
-            mix(m);
+            mix(m, xd);
         }
         if (out_peak != nullptr) {
             pk = warp_max(pk);
