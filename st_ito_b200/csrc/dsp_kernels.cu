@@ -1244,8 +1244,11 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"((uint32_t)(8 * S * 4)) : "memory");
             }
             __syncwarp();
+            // relaxed: a release here would first drain these threads' just-issued global stores of the mix (~1 us, and the
+            // whole group then waits for them at the next barrier); what has to be ordered -- every thread's READS of
+            // dly[.][slot] -- completed before the barrier above
             if (a < NSPLIT)
-                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_of[a] + 8u * slot) : "memory");
+                asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_of[a] + 8u * slot) : "memory");
         }
         for (int64_t m = max((int64_t)0, nsteps - 2); m < nsteps; ++m) {  // the last two super-steps are still unmixed
             float xd[kPerA];
