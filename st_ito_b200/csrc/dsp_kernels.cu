@@ -1209,15 +1209,22 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
                 const int off = sb * kRevSub + a;
                 if (off < S) {
                     const int n = nbase + off;
+                    // all 12 shared-memory loads up front: the four all-pass rings are distinct arrays and each stage reads
+                    // >= 244 samples behind what this sub-block writes, but the compiler cannot know and would serialise every
+                    // stage's load behind the previous stage's store (4 x ~30 cycles of latency on the critical chain)
+                    float cr[8], bvv[4];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) cr[j] = row[j * kRsDepth * kRevMaxS + off];
+#pragma unroll
+                    for (int s2 = 0; s2 < 4; ++s2) bvv[s2] = ap[s2 * kApRing + ((n - ad[s2]) & (kApRing - 1))];
                     float v = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v = __fadd_rn(v, row[j * kRsDepth * kRevMaxS + off]);
+                    for (int j = 0; j < 8; ++j) v = __fadd_rn(v, cr[j]);
 #pragma unroll
                     for (int s2 = 0; s2 < 4; ++s2) {
-                        const float bv = ap[s2 * kApRing + ((n - ad[s2]) & (kApRing - 1))];
-                        const float tv = undenorm(__fadd_rn(v, __fmul_rn(bv, 0.5f)));
+                        const float tv = undenorm(__fadd_rn(v, __fmul_rn(bvv[s2], 0.5f)));
                         ap[s2 * kApRing + (n & (kApRing - 1))] = tv;
-                        v = __fsub_rn(bv, v);
+                        v = __fsub_rn(bvv[s2], v);
                     }
                     wown[off] = v;
                 }
