@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU session E: split reverb with bulk-copy DSMEM hand-off
 cd "$(dirname "$0")/.."
-mkdir -p gpurun_out
+mkdir -p gpurun_out; md5sum st_ito_b200/libstito.so
 timeout 900 python -m pytest tests -m gpu -x -q -k "config2_full or single_plugin or ragged or other_sample_rates or properties_at_full" > gpurun_out/e_gpu_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/e_gpu_tests.log
 for p in 8 12; do
   timeout 300 python bench.py --pop $p --steps 2 --warmup 1 --no-cpu-baseline >> gpurun_out/e_pop_sweep.jsonl 2>> gpurun_out/e_bench.err

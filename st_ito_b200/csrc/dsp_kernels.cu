@@ -943,12 +943,13 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
 //     producers.  A ring of kRsDepth slots decouples the two sides: there is no CTA-wide barrier in the loop.
 // Per super-step both sides are chain-bound at ~0.8 us instead of issue-bound at 2.2 us.
 constexpr int kRsDepth = 3;
-template <int NSPLIT> struct RsCfg {
-    static constexpr int CW = 8 / NSPLIT;
-    static constexpr int kCombThreads = 32 * CW;
+template <int NSPLIT, int WPC> struct RsCfg {
+    static constexpr int CW = 8 / NSPLIT;                  // comb filters per CTA
+    static constexpr int kCombThreads = 32 * WPC * CW;     // WPC warps per comb filter
     static constexpr int kThreads = kCombThreads + kRevSub;
     static constexpr int kFloats = CW * kCombRing + 8 * kRsDepth * kRevMaxS + 4 * kApRing + 2 * kRevMaxS + 6 * kRevMaxS +
-                                   CW * kRsDepth * kRevMaxS;  // last term: staging of the delayed rows (source of the bulk copies)
+                                   CW * kRsDepth * kRevMaxS +  // staging of the delayed rows (source of the bulk copies)
+                                   2 * CW * WPC * 2 + 2 * CW;  // per-warp scan totals (double-buffered float2) + carries
     static constexpr size_t kSmem = (size_t)kFloats * sizeof(float) + 9 * sizeof(uint64_t) + 16;
 };
 
@@ -971,12 +972,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     }
 }
 
-template <int SEG, int NSPLIT>
-__global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kernel(SigView in, float *out, int64_t L,
-                                                                                 ReverbFastGeom g, const ReverbParams *prm,
-                                                                                 unsigned *out_peak, const int *ready) {
-    using Cfg = RsCfg<NSPLIT>;
-    constexpr int CW = Cfg::CW, S = 32 * SEG, RL = 3 * S;
+// SEGL samples per lane, WPC warps per comb filter: S = 32 * WPC * SEGL samples per super-step (7 x 5 -> 1120, 8 x 4 -> 1024)
+template <int SEGL, int WPC, int NSPLIT>
+__global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_kernel(SigView in, float *out, int64_t L,
+                                                                                      ReverbFastGeom g, const ReverbParams *prm,
+                                                                                      unsigned *out_peak, const int *ready) {
+    using Cfg = RsCfg<NSPLIT, WPC>;
+    constexpr int CW = Cfg::CW, S = 32 * WPC * SEGL, RL = 3 * S;
     constexpr int nsub = (S + kRevSub - 1) / kRevSub;
     extern __shared__ float sm[];
     float *ring = sm;                                   // [CW][kCombRing] my comb filters
@@ -985,7 +987,9 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
     float *inbuf = ap + 4 * kApRing;                    // [2][kRevMaxS] reverb input (l + r) * 0.015 of super-steps k, k + 1
     float *wetb = inbuf + 2 * kRevMaxS;                 // [3][2][kRevMaxS] wet rows of super-steps k, k - 1, k - 2: [k % 3][own, peer]
     float *stage = wetb + 6 * kRevMaxS;                 // [CW][kRsDepth][kRevMaxS] delayed rows staged for the bulk copy
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + CW * kRsDepth * kRevMaxS);  // full[3], free[3], xbar[3]
+    float *wtot = stage + CW * kRsDepth * kRevMaxS;     // [2][CW][WPC] float2: affine map of each warp's part of the damping scan
+    float *carry = wtot + 2 * CW * WPC * 2;             // [2][CW] damping-filter state entering the next super-step
+    uint64_t *bars = reinterpret_cast<uint64_t *>(carry + 2 * CW);  // full[3], free[3], xbar[3]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = blockIdx.x % (2 * NSPLIT);
     const int p = blockIdx.x / (2 * NSPLIT);
@@ -1034,20 +1038,23 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
 
     if (tid < Cfg::kCombThreads) {
         // ------------------------------------------------------------------ comb group (producer)
-        const int jg = gq * CW + warp;                 // global comb index 0..7 of channel c
+        // One comb filter = WPC warps; lane l = ww * 32 + lane of the comb owns SEGL consecutive samples of the super-step.
+        // (One warp per comb with 35 samples per lane is a ~980-instruction dependent chain per super-step -- 2 us, which
+        // is what bounds reverb_core_kernel as well; ncu source view in profiles/r02e_reverb_split.md.)
+        const int cw = warp / WPC, ww = warp % WPC;
+        const int jg = gq * CW + cw;                   // global comb index 0..7 of channel c
         const int my_delay = g.comb_delay[c][jg];
-        float *my_ring = ring + warp * kCombRing;
+        float *my_ring = ring + cw * kCombRing;
         const float keep = __fsub_rn(1.0f, q.damp);
-        float fstore = 0.0f, dpow = 1.0f;
+        float dpow = 1.0f;
 #pragma unroll
-        for (int i = 0; i < SEG; ++i) dpow = __fmul_rn(dpow, q.damp);
-        const int i0 = lane * SEG;
+        for (int i = 0; i < SEGL; ++i) dpow = __fmul_rn(dpow, q.damp);
+        const int lc = ww * 32 + lane;                 // lane index inside the comb
+        const int i0 = lc * SEGL;
         const uint32_t dly_home = map_to((uint32_t)__cvta_generic_to_shared(dly), home_rank);
         const uint32_t full_home = map_to(bar0, home_rank);
-        constexpr int kPreC = (2 * kRevMaxS + Cfg::kCombThreads - 1) / Cfg::kCombThreads;  // samples (l and r) per thread
         // stage the reverb input of one super-step: thread t handles flat indices t, t + T, ... of [S] (l, r summed)
         constexpr int kPerT = (kRevMaxS + Cfg::kCombThreads - 1) / Cfg::kCombThreads;
-        (void)kPreC;
         float pl[kPerT], pr[kPerT];
         auto fetch_in = [&](int64_t base) {
 #pragma unroll
@@ -1068,33 +1075,35 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
             }
         };
         auto comb_bar = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(Cfg::kCombThreads) : "memory"); };
-        // delayed outputs for the all-pass chain of super-step m -> home CTA's dly[jg][m % depth], then arrive on full
-        auto emit = [&](int64_t m) {
+        // Delayed outputs for the all-pass chain of super-step m: the S samples are one contiguous run of my ring (it
+        // continues into the mirror, never wraps).  The comb's warps copy it into a 16-byte aligned staging row
+        // (stage_row); after the next CTA barrier ONE lane hands the row to the bulk-copy engine (ship_row), which writes the
+        // home CTA's dly row through distributed shared memory and completes the transaction on the home's full[slot]
+        // mbarrier -- no remote stores and no release fence on the comb filters' critical path.  The staging row is reused
+        // for super-step m + depth, i.e. only after free[slot] said that the all-pass group has consumed this one.
+        auto stage_row = [&](int64_t m) {
             const int slot = (int)(m % kRsDepth);
             if (m >= kRsDepth)  // the home's all-pass group must have finished super-step m - depth (which read this slot)
                 mbar_wait_cluster(bar0 + 8u * (kRsDepth + slot), (uint32_t)(((m / kRsDepth) - 1) & 1));
             const int wb = (int)(m % 3) * S;
             int rb = wb - my_delay;
             if (rb < 0) rb += RL;
-            // The S delayed samples are one contiguous run of my ring (it continues into the mirror, never wraps).  The warp
-            // copies it into a 16-byte aligned staging row and ONE lane hands it to the bulk-copy engine, which writes the
-            // home CTA's dly row through distributed shared memory and completes the transaction on the home's full[slot]
-            // mbarrier -- no remote stores and no release fence on the comb filters' critical path (they cost ~1 us per
-            // super-step: ncu source view of the first version, profiles/r02d_*).  The staging row is reused for super-step
-            // m + depth, i.e. only after free[slot] said that the all-pass group has consumed this one.
             const float *rp = my_ring + rb;
-            float *srow = stage + (warp * kRsDepth + slot) * kRevMaxS;
+            float *srow = stage + (cw * kRsDepth + slot) * kRevMaxS;
 #pragma unroll
-            for (int t = 0; t < (S / 4 + 31) / 32; ++t) {
-                const int v4 = lane + 32 * t;
+            for (int t = 0; t < (S / 4 + 32 * WPC - 1) / (32 * WPC); ++t) {
+                const int v4 = lc + 32 * WPC * t;
                 if (v4 < S / 4) {
                     const float *src = rp + 4 * v4;
                     *reinterpret_cast<float4 *>(srow + 4 * v4) = make_float4(src[0], src[1], src[2], src[3]);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my staging writes -> visible to the async proxy
-            __syncwarp();
-            if (lane == 0) {
+        };
+        auto ship_row = [&](int64_t m) {  // after a CTA barrier that follows stage_row(m)
+            if (lc == 0) {
+                const int slot = (int)(m % kRsDepth);
+                const float *srow = stage + (cw * kRsDepth + slot) * kRevMaxS;
                 const uint32_t dst = dly_home + (uint32_t)((jg * kRsDepth + slot) * kRevMaxS) * 4u;
                 asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(dst), "r"((uint32_t)__cvta_generic_to_shared(srow)), "r"((uint32_t)(S * 4)), "r"(full_home + 8u * slot)
@@ -1105,45 +1114,54 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT>::kThreads, 1) reverb_split_kerne
         if (ready != nullptr) comb_bar();
         fetch_in(0);
         park_in(0);
+        stage_row(0);  // all zeros: nothing has been written to the rings yet
+        if (lc == 0) { carry[cw] = 0.0f; carry[CW + cw] = 0.0f; }
         comb_bar();
-        emit(0);  // all zeros: nothing has been written to the rings yet
         int wbase = 0;
         for (int64_t k = 0; k < nsteps; ++k, wbase = (wbase == 2 * S) ? 0 : wbase + S) {
+            const int par = (int)(k & 1);
             fetch_in((k + 1) * S);  // next super-step's input: the loads fly during this one
-            const float *inb = inbuf + (int)(k & 1) * kRevMaxS;
+            const float *inb = inbuf + par * kRevMaxS;
             int rb = wbase - my_delay;
             if (rb < 0) rb += RL;
             const float *rp = my_ring + rb + i0;
             float *wp = my_ring + wbase + i0;
-            float o[SEG];
+            float o[SEGL];
 #pragma unroll
-            for (int i = 0; i < SEG; ++i) o[i] = rp[i];
-            float z = 0.0f;
+            for (int i = 0; i < SEGL; ++i) o[i] = rp[i];
+            float z = 0.0f;  // zero-state response of the damping one-pole over my segment
 #pragma unroll
-            for (int i = 0; i < SEG; ++i) z = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(z, q.damp)));
-            float A = dpow, Bv = z;
+            for (int i = 0; i < SEGL; ++i) z = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(z, q.damp)));
+            float A = dpow, Bv = z;  // affine map of my segment: s -> A * s + Bv; inclusive scan over the warp
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const float Ap = __shfl_up_sync(0xffffffffu, A, d);
                 const float Bp = __shfl_up_sync(0xffffffffu, Bv, d);
                 if (lane >= d) { Bv = fmaf(Bp, A, Bv); A = A * Ap; }
             }
-            const float s_out = fmaf(A, fstore, Bv);
-            float sv = __shfl_up_sync(0xffffffffu, s_out, 1);
-            if (lane == 0) sv = fstore;
+            float2 *wt = reinterpret_cast<float2 *>(wtot) + (par * CW + cw) * WPC;
+            if (lane == 31) wt[ww] = make_float2(A, Bv);
+            comb_bar();                 // (A) warp totals + last step's carry visible; the staged row of step k is complete
+            ship_row(k);
+            float s_in = carry[par * CW + cw];  // state entering this super-step, then through the warps before mine
 #pragma unroll
-            for (int i = 0; i < SEG; ++i) {
+            for (int w2 = 0; w2 < WPC - 1; ++w2)
+                if (w2 < ww) { const float2 t = wt[w2]; s_in = fmaf(t.x, s_in, t.y); }
+            const float s_out = fmaf(A, s_in, Bv);
+            float sv = __shfl_up_sync(0xffffffffu, s_out, 1);
+            if (lane == 0) sv = s_in;
+#pragma unroll
+            for (int i = 0; i < SEGL; ++i) {
                 sv = undenorm(__fadd_rn(__fmul_rn(o[i], keep), __fmul_rn(sv, q.damp)));
                 const float tv = undenorm(__fadd_rn(inb[i0 + i], __fmul_rn(sv, q.fb)));
                 wp[i] = tv;
                 if (wbase == 0) wp[RL + i] = tv;  // keep the mirror of the ring head current
             }
-            fstore = __shfl_sync(0xffffffffu, sv, 31);
-            __syncwarp();
-            if (k + 1 < nsteps) emit(k + 1);
-            park_in((int)((k + 1) & 1));
+            if (ww == WPC - 1 && lane == 31) carry[(par ^ 1) * CW + cw] = sv;
+            park_in(par ^ 1);
             if (ready != nullptr && tid == 0) need_input((k + 3) * (int64_t)S);
-            comb_bar();
+            comb_bar();                 // (B) ring writes of this super-step visible to every warp of the comb
+            if (k + 1 < nsteps) stage_row(k + 1);  // shipped after barrier (A) of the next iteration
         }
     } else if (home) {
         // ------------------------------------------------------------------ all-pass group of the home CTA (consumer)
@@ -1430,13 +1448,16 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
         static const bool split_on = !(getenv("STITO_REVERB_SPLIT") && atoi(getenv("STITO_REVERB_SPLIT")) == 0);
         if (split_on && pair && in_peak == nullptr && P * 8 <= sm_budget) {
             using KernS = void (*)(SigView, float *, int64_t, ReverbFastGeom, const ReverbParams *, unsigned *, const int *);
-            KernS ks = seg == kRevMaxSegF ? reverb_split_kernel<kRevMaxSegF, 4> : reverb_split_kernel<32, 4>;
-            const size_t ssm = RsCfg<4>::kSmem;
+            constexpr int kWpcA = 5, kWpcB = 4;  // 7 samples x 160 lanes = 1120; 8 x 128 = 1024
+            static_assert(32 * kWpcA * 7 == 32 * kRevMaxSegF && 32 * kWpcB * 8 == 32 * 32, "super-step lengths");
+            const bool big = seg == kRevMaxSegF;
+            KernS ks = big ? reverb_split_kernel<7, kWpcA, 4> : reverb_split_kernel<8, kWpcB, 4>;
+            const size_t ssm = big ? RsCfg<4, kWpcA>::kSmem : RsCfg<4, kWpcB>::kSmem;
             e = ensure_dyn_smem(reinterpret_cast<const void *>(ks), (int)ssm);
             if (e != cudaSuccess) return e;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(P * 8);
-            cfg.blockDim = dim3(RsCfg<4>::kThreads);
+            cfg.blockDim = dim3(big ? RsCfg<4, kWpcA>::kThreads : RsCfg<4, kWpcB>::kThreads);
             cfg.dynamicSmemBytes = ssm;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];

@@ -674,9 +674,15 @@ def test_config2_full_size_population_vs_oracle(models_centred, oracle_dsp):
     # config 3: 256 candidates over 8 GPUs = shards of 32; a shard scored alone equals its rows of the whole population
     f_shard, e_shard, _ = eng.eval_population(W[32:], 0, L, want_embeds=True)
     assert torch.equal(f_shard, fit[32:]) and torch.equal(e_shard, emb[:, 32:])
-    f8, _, aud8 = eng.eval_population(W[:8], 0, L, want_audio=True, in_chs=2)  # the 8-per-GPU shard of pop = 64 on 8 GPUs
-    assert torch.equal(f8, fit[:8])
+    # the 8-per-GPU shard of pop = 64 on 8 GPUs: small populations take the streaming compressor -> reverb pair and the
+    # cluster-split Freeverb, whose damping scan is partitioned over 160 lanes instead of 32 (different rounding of the
+    # predicted segment states): equal to the large-population kernels to float32 rounding noise, and deterministic
+    f8, _, aud8 = eng.eval_population(W[:8], 0, L, want_audio=True, in_chs=2)
+    np.testing.assert_allclose(f8.numpy(), fit[:8].numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(np.argsort(f8.numpy(), kind="stable"), np.argsort(want[:8], kind="stable"))
     assert np.abs(aud8.numpy() - audios.numpy()).max() <= 3e-5
+    f8b, _, _ = eng.eval_population(W[:8], 0, L)
+    assert torch.equal(f8, f8b)
 
 
 def test_config1_as_stated_vs_oracle(models_centred, oracle_dsp):
