@@ -1117,6 +1117,7 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
         stage_row(0);  // all zeros: nothing has been written to the rings yet
         if (lc == 0) { carry[cw] = 0.0f; carry[CW + cw] = 0.0f; }
         comb_bar();
+        ship_row(0);
         int wbase = 0;
         for (int64_t k = 0; k < nsteps; ++k, wbase = (wbase == 2 * S) ? 0 : wbase + S) {
             const int par = (int)(k & 1);
@@ -1141,8 +1142,7 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
             }
             float2 *wt = reinterpret_cast<float2 *>(wtot) + (par * CW + cw) * WPC;
             if (lane == 31) wt[ww] = make_float2(A, Bv);
-            comb_bar();                 // (A) warp totals + last step's carry visible; the staged row of step k is complete
-            ship_row(k);
+            comb_bar();                 // (A) warp totals + last step's carry visible
             float s_in = carry[par * CW + cw];  // state entering this super-step, then through the warps before mine
 #pragma unroll
             for (int w2 = 0; w2 < WPC - 1; ++w2)
@@ -1161,7 +1161,11 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
             park_in(par ^ 1);
             if (ready != nullptr && tid == 0) need_input((k + 3) * (int64_t)S);
             comb_bar();                 // (B) ring writes of this super-step visible to every warp of the comb
-            if (k + 1 < nsteps) stage_row(k + 1);  // shipped after barrier (A) of the next iteration
+            if (k + 1 < nsteps) {       // the row the all-pass chain needs next: stage it and ship it at once -- the hand-off
+                stage_row(k + 1);       // loop (row -> all-passes -> free -> next row of the slot) is latency-bound, every
+                comb_bar();             // microsecond in it costs a third of a microsecond per super-step
+                ship_row(k + 1);
+            }
         }
     } else if (home) {
         // ------------------------------------------------------------------ all-pass group of the home CTA (consumer)
