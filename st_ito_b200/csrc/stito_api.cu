@@ -182,6 +182,7 @@ struct stito_handle {
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     HostBuf hparams, hW, hflags;
+    size_t hparams_cursor = 0;  // every micro-batch of a call designs into its own slice of the pinned staging buffer
     // flags (device ints): [0], [1] NaN in mid / side embeddings; [2] an activation left the fp16 range of the fp16x3
     // encoder; [3] compressor super-blocks redone serially (Newton iteration did not converge)
     //        [4..15] per conv layer: float bits of the largest stored activation (tensor-core path)
@@ -386,11 +387,21 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
     }
     // parameters: host design -> one H2D copy
     const size_t pbytes = (size_t)c.num_fx * P * kParamSlot;
-    CU(h->hparams.ensure(pbytes));
+    // The H2D copy below is asynchronous: with three or more micro-batches in flight the host would otherwise overwrite the
+    // pinned staging block of micro-batch i + 1 (whose copy is queued behind the kernels of micro-batch i) with the parameters
+    // of micro-batch i + 2.  Every micro-batch of a call therefore gets its own slice (the caller reserved the capacity and
+    // reset the cursor); if the slices are exhausted, drain the stream and start over.
+    if (h->hparams_cursor + pbytes > h->hparams.cap) {
+        CU(cudaStreamSynchronize(st));
+        h->hparams_cursor = 0;
+        CU(h->hparams.ensure(pbytes));
+    }
+    uint8_t *hslice = h->hparams.as<uint8_t>() + h->hparams_cursor;
+    h->hparams_cursor += (pbytes + 255) & ~(size_t)255;
     CU(h->params.ensure(pbytes));
     int max_d = 1;
-    design_params(c, W_host, P, D, h->hparams.as<uint8_t>(), &max_d);
-    CU(cudaMemcpyAsync(h->params.p, h->hparams.p, pbytes, cudaMemcpyHostToDevice, st));
+    design_params(c, W_host, P, D, hslice, &max_d);
+    CU(cudaMemcpyAsync(h->params.p, hslice, pbytes, cudaMemcpyHostToDevice, st));
 
     SigView cur = in;
     int cur_chs = chs;
@@ -790,6 +801,12 @@ static int enqueue_population(stito_handle *h, cudaStream_t st, const double *Wh
     int launches = 0;
     SigView in{h->input.as<float>() + start, 0, h->in_cap};
     CU(cudaMemsetAsync(h->flags.as<int>() + 2, 0, (kNumFlags - 2) * sizeof(int), st));
+    {   // pinned parameter staging for ALL micro-batches of this call (see run_chain); nothing of it is in flight here
+        const size_t nmb = (size_t)(P + h->microbatch - 1) / h->microbatch;
+        const size_t per = (((size_t)h->chain.num_fx * (P < h->microbatch ? P : h->microbatch) * kParamSlot) + 255) & ~(size_t)255;
+        CU(h->hparams.ensure(nmb * per + 256));
+        h->hparams_cursor = 0;
+    }
     CU(cudaEventRecord(h->ev[0], st));
     for (int p0 = 0; p0 < P; p0 += h->microbatch) {
         const int pb = (P - p0) < h->microbatch ? (P - p0) : h->microbatch;
@@ -913,6 +930,7 @@ int stito_process(stito_handle *h, const float *x, int chs, int64_t L, const dou
         const float *res = nullptr;
         const unsigned *pk = nullptr;
         int ych = 0;
+        h->hparams_cursor = 0;  // the previous micro-batch was synchronised below
         rc = run_chain(h, st, in, chs, L, Wh ? Wh + (size_t)p0 * D : nullptr, pb, D, &res, &pk, &ych, &launches);
         if (rc) return rc;
         float *dst = y + (size_t)p0 * ochs * L;

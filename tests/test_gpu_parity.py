@@ -994,3 +994,27 @@ def test_config4_as_stated_30s_conv_reverb(models_centred, oracle_dsp):
     err = np.abs(aud[0].numpy() - ref0)
     assert err.max() <= 3e-5 and err.mean() <= 5e-6, (err.max(), err.mean())
     np.testing.assert_array_equal(aud[2].numpy(), tgt)
+
+
+def test_many_microbatches_equal_separate_calls(models_centred):
+    """Populations larger than two micro-batches (P > 128): every micro-batch must be rendered with ITS OWN parameters.
+    (Round 1 designed all micro-batches into one pinned staging block while the asynchronous upload of the previous one was
+    still queued -- found by bench.py's shard check at pop = 256 in round 2.)"""
+    from st_ito_b200.engine import compile_chain
+
+    ours, _ = models_centred
+    eng = ours.stito_engine()
+    eng.set_precision(1)
+    plugins, D, _ = native_plugins(["eq", "comp", "reverb"])
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    L = 40000
+    x = test_signal(2, L, seed=77)
+    x = x / np.abs(x).max()
+    eng.set_input(x)
+    eng.set_target(x)
+    W = np.random.RandomState(78).rand(200, D)
+    whole, emb, _ = eng.eval_population(W, 0, L, want_embeds=True)
+    parts = torch.cat([eng.eval_population(W[i:i + 64], 0, L)[0] for i in range(0, 200, 64)])
+    assert torch.equal(whole, parts)
+    assert len(set(np.round(whole.numpy(), 6))) > 150  # and they really are 200 different candidates
