@@ -26,7 +26,7 @@ for r in rows[-n_last:]:
 out.append(f"TOTAL,,,{tot:.1f}")
 open(os.path.join(ROOT, "profiles", f"{tag}_generation_kernels.csv"), "w").write("\n".join(out) + "\n")
 
-raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True)
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True)
 rr = list(csv.reader(raw.splitlines()))
 hdr, units = rr[0], rr[1]
 want = ["ID", "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum",
@@ -37,7 +37,7 @@ want = ["ID", "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum"
 idx = [hdr.index(w) for w in want if w in hdr]
 with open(os.path.join(ROOT, "profiles", f"{tag}_conv_ncu_full_summary.csv"), "w") as f:
     w = csv.writer(f)
-    w.writerow([f"# {tag}: ncu --set full --clock-control none -k regex:conv3x3 (the 11 tensor-core conv launches of one "
+    w.writerow([f"# {tag}: ncu --set full --clock-control none -k regex:conv3x3|wino (the conv-stack launches of one "
                 "generation, P=64, 10 s stereo); second row = units"])
     w.writerow([hdr[i] for i in idx])
     w.writerow([units[i] for i in idx])

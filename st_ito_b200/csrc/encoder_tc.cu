@@ -207,7 +207,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 template <int kCols>
 __device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&acc)[kCols], int nt, int mt,
                                            int tiles_per_group, int img, int rr, int cc, int BN, int col0,
-                                           const float *sbias) {
+                                           const float *sbias, float &mx) {
     const int grp = mt / tiles_per_group, rem = mt - grp * tiles_per_group;
     const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
     const int n0 = grp * p.IPT, h0 = th * p.BH, w0 = tw * p.BW;
@@ -226,7 +226,6 @@ __device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&
         store = img < p.IPT && (n0 + img) < p.N && hh < p.H && ww < p.W;
         obase = (((int64_t)(n0 + img) * p.H + hh) * p.W + ww) * p.Cout + cbase;
     }
-    float mx = 0.0f;
 #pragma unroll
     for (int j0 = 0; j0 < kCols; j0 += 8) {
         float y[8];
@@ -269,7 +268,6 @@ __device__ __forceinline__ void store_tile(const ConvTcParams &p, const float (&
             *reinterpret_cast<uint4 *>(p.out_lo + obase + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
-    if (p.out_f32 == nullptr) publish_amax(p.amax, mx);  // every lane of the warp gets here (uniform call sites)
 }
 
 // Persistent, warp-specialised implicit-GEMM convolution.
@@ -437,6 +435,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
         const int r = m - img * per_img;
         const int rr = r / p.BW, cc = r - rr * p.BW;
         uint32_t c = 0;
+        float amax_run = 0.0f;  // largest value this thread stored (for the activation-scale calibration)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             float acc[kCols];
 #pragma unroll
@@ -471,9 +470,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_tc_kernel(const __gri
                 continue;
             }
             const int nt = tile / mgroups, mg = tile - nt * mgroups;
-            if (MT == 1) store_tile<kCols>(p, acc, nt, mg, tiles_per_group, img, rr, cc, BN, half * kCols, sbias);
-            else store_tile<kCols>(p, acc, nt, mg * MT + half, tiles_per_group, img, rr, cc, BN, 0, sbias);
+            if (MT == 1) store_tile<kCols>(p, acc, nt, mg, tiles_per_group, img, rr, cc, BN, half * kCols, sbias, amax_run);
+            else store_tile<kCols>(p, acc, nt, mg * MT + half, tiles_per_group, img, rr, cc, BN, 0, sbias, amax_run);
         }
+        // one atomic per warp and KERNEL (a per-tile atomicMax on one address from 60 k warps-tiles cost ~5 % of block 1)
+        if (!p.gemm && p.out_f32 == nullptr) publish_amax(p.amax, amax_run);
     }
     tc_fence_before();
     __syncthreads();
@@ -593,6 +594,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_c64_kernel(const __gr
         const int m = q * 32 + lane;
         const int rr = m / p.BW, cc = m - rr * p.BW;
         uint32_t c = 0;
+        float amax_run = 0.0f;  // largest value this thread stored (for the activation-scale calibration)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             float acc[kCols];
 #pragma unroll
@@ -615,8 +617,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_c64_kernel(const __gr
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
             }
-            store_tile<kCols>(p, acc, 0, tile, tiles_per_group, 0, rr, cc, BN, half * kCols, sbias);
+            store_tile<kCols>(p, acc, 0, tile, tiles_per_group, 0, rr, cc, BN, half * kCols, sbias, amax_run);
         }
+        if (p.out_f32 == nullptr) publish_amax(p.amax, amax_run);
     }
     tc_fence_before();
     __syncthreads();
@@ -1012,13 +1015,19 @@ int ws_ensure(TcWorkspace &ws, int i, size_t bytes) {
 }
 
 // K-slabs (of 64) accumulated in TMEM between fp32 drains; STITO_TC_CHUNK overrides (developer knob)
-int chunk_slabs() {
-    static int v = 0;
+int chunk_slabs(int BN = 256) {
+    // K = 128 per chunk: the 1e-4 gate then holds WITHOUT the accumulate compensation (see chunk_comp()).  The N = 128 layers
+    // (block 2) drain twice as often per MMA cycle as the N = 256 ones, where K = 128 chunks cost +19 % / +11 %: they use
+    // K = 192 (the same number of drains as K = 256 on their K = 576 / 1152 loops, but balanced).  STITO_TC_CHUNK overrides
+    // both, STITO_TC_CHUNK128 the N <= 128 value (developer knobs).
+    static int v = 0, v128 = 0;
     if (v == 0) {
-        v = 2;  // K = 128 per chunk: the 1e-4 gate then holds WITHOUT the accumulate compensation (see chunk_comp())
-        if (const char *e = getenv("STITO_TC_CHUNK")) { const int t = atoi(e); if (t > 0) v = t; }
+        v = 2;
+        v128 = 3;
+        if (const char *e = getenv("STITO_TC_CHUNK")) { const int t = atoi(e); if (t > 0) v = v128 = t; }
+        if (const char *e = getenv("STITO_TC_CHUNK128")) { const int t = atoi(e); if (t > 0) v128 = t; }
     }
-    return v;
+    return BN <= 128 ? v128 : v;
 }
 
 int slab_k(int cin) {
@@ -1247,7 +1256,7 @@ static int conv_tc(cudaStream_t st, const ConvLayer &l, TcWorkspace &ws, int li,
     // K-slab per ring stage: 32 (64-byte swizzle, twice as many stages in the same shared memory: the producer runs
     // further ahead of the MMA issuer) or 64 (128-byte swizzle), chosen per layer; STITO_TC_SLABK overrides
     const int slabk = slab_k(l.cin);
-    p.chunk_slabs = chunk_slabs() * (64 / slabk);
+    p.chunk_slabs = chunk_slabs(BN) * (64 / slabk);
     if (!(ah = make_act_map(ws, in_hi, N, H, W, l.cin, p.BW, p.BH, p.IPT, slabk))) return -1;
     if (!(al = make_act_map(ws, in_lo, N, H, W, l.cin, p.BW, p.BH, p.IPT, slabk))) return -1;
     if (!(bh_ = make_w_map(ws, l.w_hi, l.cout, 9 * l.cin, BN, slabk))) return -1;

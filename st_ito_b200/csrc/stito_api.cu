@@ -198,6 +198,7 @@ struct stito_handle {
     cudaEvent_t ev_conv[13] = {};
     stito_timing timing{};
     bool timing_pending = false;
+    double timing_scale = 1.0;
 };
 
 // After a synchronised pass of the tensor-core encoder: calibrate the per-layer storage scales of the fp16 hi/lo
@@ -855,6 +856,7 @@ int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_
     if (fitness && !h->has_target) return fail(STITO_ESTATE, "no target set (stito_set_target / stito_set_target_embeds)");
     if (start < 0 || len <= 0 || start + len > h->in_cap) return fail(STITO_EINVAL, "view [%lld, %lld) outside the padded input of %lld samples", (long long)start, (long long)(start + len), (long long)h->in_cap);
     if (P == 0) {  // an empty shard of a sharded population (more ranks than candidates): nothing to do, nothing written
+        h->timing_pending = false;
         memset(&h->timing, 0, sizeof(h->timing));
         h->timing.precision = h->precision;
         return STITO_OK;
@@ -880,22 +882,10 @@ int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_
         ++overflowed;
     }
     h->comp_fallbacks_total += comp_fallbacks;
-    // timing of this call
+    // Timing of this call: the 17 cudaEventElapsedTime queries (~50 us of host time, every generation) are deferred to
+    // stito_get_timing(); only what cannot be recomputed later is stored here.
     stito_timing &t = h->timing;
     memset(&t, 0, sizeof(t));
-    const int pb0 = P < h->microbatch ? P : h->microbatch;
-    const double scale = (double)P / pb0;  // stage times are measured on the first micro-batch
-    cudaEventElapsedTime(&t.ms_dsp, h->ev[0], h->ev[1]);
-    cudaEventElapsedTime(&t.ms_frontend, h->ev[2], h->ev[3]);
-    cudaEventElapsedTime(&t.ms_encoder, h->ev[3], h->ev[4]);
-    cudaEventElapsedTime(&t.ms_fitness, h->ev[5], h->ev[6]);
-    cudaEventElapsedTime(&t.ms_total, h->ev[0], h->ev[6]);
-    t.ms_dsp *= (float)scale; t.ms_frontend *= (float)scale; t.ms_encoder *= (float)scale;
-    for (int l = 0; l < 12; ++l) {
-        cudaEventElapsedTime(&t.ms_conv[l], h->ev_conv[l], h->ev_conv[l + 1]);
-        t.ms_conv[l] *= (float)scale;
-    }
-    cudaGetLastError();
     t.launches = launches;
     t.precision = h->precision;
     t.comp_fallbacks = comp_fallbacks;
@@ -904,6 +894,8 @@ int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_
     t.encoder_flop = encoder_flops(P * ochs, T, h->n_mels);
     t.dsp_bytes = 4.0 * chs * len + 4.0 * ochs * len * P;
     t.frontend_bytes = P * (4.0 * ochs * len + (double)ochs * T * h->n_mels * 4.0);
+    h->timing_pending = true;
+    h->timing_scale = (double)P / (P < h->microbatch ? P : h->microbatch);  // stage times are measured on the first micro-batch
     return STITO_OK;
 }
 
@@ -952,6 +944,7 @@ int stito_process(stito_handle *h, const float *x, int chs, int64_t L, const dou
     }
     CU(cudaMemcpyAsync(h->hflags.p, h->flags.p, kNumFlags * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    h->timing_pending = false;
     memset(&h->timing, 0, sizeof(h->timing));
     h->timing.launches = launches;
     h->timing.precision = h->precision;
@@ -1000,6 +993,7 @@ int stito_embed(stito_handle *h, const float *x, int B, int chs, int64_t L, int 
         if (!tc_after_pass(h)) break;  // else: activation scales re-calibrated -> once more
         ++overflowed;
     }
+    h->timing_pending = false;
     memset(&h->timing, 0, sizeof(h->timing));
     h->timing.launches = launches;
     h->timing.precision = h->precision;
@@ -1031,8 +1025,25 @@ int stito_logmel(stito_handle *h, const float *x, int B, int chs, int64_t L, flo
     return STITO_OK;
 }
 
-int stito_get_timing(const stito_handle *h, stito_timing *out) {
-    if (!h || !out) return fail(STITO_EINVAL, "NULL argument");
+int stito_get_timing(const stito_handle *hc, stito_timing *out) {
+    if (!hc || !out) return fail(STITO_EINVAL, "NULL argument");
+    stito_handle *h = const_cast<stito_handle *>(hc);
+    if (h->timing_pending) {  // events of the last stito_eval_population (it synchronised the stream before returning)
+        stito_timing &t = h->timing;
+        const float scale = (float)h->timing_scale;
+        cudaEventElapsedTime(&t.ms_dsp, h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&t.ms_frontend, h->ev[2], h->ev[3]);
+        cudaEventElapsedTime(&t.ms_encoder, h->ev[3], h->ev[4]);
+        cudaEventElapsedTime(&t.ms_fitness, h->ev[5], h->ev[6]);
+        cudaEventElapsedTime(&t.ms_total, h->ev[0], h->ev[6]);
+        t.ms_dsp *= scale; t.ms_frontend *= scale; t.ms_encoder *= scale;
+        for (int l = 0; l < 12; ++l) {
+            cudaEventElapsedTime(&t.ms_conv[l], h->ev_conv[l], h->ev_conv[l + 1]);
+            t.ms_conv[l] *= scale;
+        }
+        cudaGetLastError();  // precision 0 records no per-layer events
+        h->timing_pending = false;
+    }
     *out = h->timing;
     return STITO_OK;
 }
