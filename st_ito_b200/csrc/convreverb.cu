@@ -32,7 +32,7 @@ constexpr int kCrvB = kCrvN / 2;      // partition / hop
 constexpr int kCrvThreads = 1024;
 constexpr int kCrvBands = 12;
 constexpr int kCrvTaps = 1023;
-constexpr size_t kCrvSmem = (size_t)kCrvN * sizeof(float2);
+constexpr size_t kCrvSmem = (size_t)(kCrvN + kCrvN / 4) * sizeof(float2);  // data + quarter-circle twiddles
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -40,8 +40,17 @@ __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
 
 // 16384-point complex FFT (forward, e^{-i...}) of buf[] in shared memory, natural order in and out: seven radix-4
 // Stockham passes.  One buffer only (two would not fit): every pass loads its 16 inputs per thread into registers,
-// synchronises, then writes its 16 outputs.
-__device__ __forceinline__ void fft16k(float2 *buf, const float2 *__restrict__ tw, int tid) {
+// synchronises, then writes its 16 outputs.  Twiddles: the three factors of a butterfly are w, w^2, w^3 with
+// w = exp(-2 pi i k / (4 ns)), an angle in the first quadrant -> ONE read of a 4096-entry quarter-circle table that lives in
+// shared memory next to the data (tws), the other two by complex multiplication.  (The first version read all three from the
+// 128 KB global table: 84 L2-latency loads per thread and transform, 42-52 % long-scoreboard stalls in ncu, 46 us per FFT.)
+constexpr int kCrvTw = kCrvN / 4;  // quarter-circle twiddle table entries
+
+__device__ __forceinline__ void load_twiddles(float2 *tws, const float2 *__restrict__ tw, int tid) {
+    for (int i = tid; i < kCrvTw; i += kCrvThreads) tws[i] = __ldg(tw + i);  // tw[i] = exp(-2 pi i * i / N), i < N / 4
+}
+
+__device__ __forceinline__ void fft16k(float2 *buf, const float2 *tws, int tid) {
     constexpr int Q = kCrvN / 4;
     constexpr int PER = Q / kCrvThreads;  // 4 butterflies per thread and pass
 #pragma unroll 1
@@ -60,9 +69,11 @@ __device__ __forceinline__ void fft16k(float2 *buf, const float2 *__restrict__ t
             const int k = j & (ns - 1);
             float2 v0 = v[it][0], v1 = v[it][1], v2 = v[it][2], v3 = v[it][3];
             if (ns > 1) {
-                v1 = cmulf(v1, __ldg(tw + k * step));
-                v2 = cmulf(v2, __ldg(tw + 2 * k * step));
-                v3 = cmulf(v3, __ldg(tw + 3 * k * step));
+                const float2 w1 = tws[k * step];  // k * step < N / 4
+                const float2 w2 = cmulf(w1, w1), w3 = cmulf(w2, w1);
+                v1 = cmulf(v1, w1);
+                v2 = cmulf(v2, w2);
+                v3 = cmulf(v3, w3);
             }
             const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y);
             const float2 t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
@@ -100,7 +111,9 @@ __global__ void __launch_bounds__(kCrvThreads, 1) crv_ir_fft_kernel(const float 
                                                                      const float2 *__restrict__ tw,
                                                                      float4 *__restrict__ H) {
     extern __shared__ float2 crv_buf[];
+    float2 *tws = crv_buf + kCrvN;
     const int part = blockIdx.x, p = blockIdx.y, tid = threadIdx.x;
+    load_twiddles(tws, tw, tid);
     const ConvRevParams q = prm[p];
     float dec[kCrvBands];
 #pragma unroll
@@ -123,7 +136,7 @@ __global__ void __launch_bounds__(kCrvThreads, 1) crv_ir_fft_kernel(const float 
         crv_buf[i] = z;
     }
     __syncthreads();
-    fft16k(crv_buf, tw, tid);
+    fft16k(crv_buf, tws, tid);
     float4 *dst = H + ((size_t)p * K + part) * (kCrvN / 2 + 1);
     for (int k = tid; k <= kCrvN / 2; k += kCrvThreads) {
         const float2 a = crv_buf[k], b = crv_buf[(kCrvN - k) & (kCrvN - 1)];
@@ -137,7 +150,9 @@ __global__ void __launch_bounds__(kCrvThreads, 1) crv_x_fft_kernel(SigView in, c
                                                                     int nblocks, const float2 *__restrict__ tw,
                                                                     float2 *__restrict__ X) {
     extern __shared__ float2 crv_buf[];
+    float2 *tws = crv_buf + kCrvN;
     const int j = blockIdx.x, p = blockIdx.y, tid = threadIdx.x;
+    load_twiddles(tws, tw, tid);
     const bool has_div = in_peak != nullptr;
     const float div = has_div ? fmaxf(in_peak[p], 1e-8f) : 1.0f;
     const float *xl = in.base + (int64_t)p * in.stride_p;
@@ -154,7 +169,7 @@ __global__ void __launch_bounds__(kCrvThreads, 1) crv_x_fft_kernel(SigView in, c
         crv_buf[i] = z;
     }
     __syncthreads();
-    fft16k(crv_buf, tw, tid);
+    fft16k(crv_buf, tws, tid);
     float2 *dst = X + ((size_t)p * nblocks + j) * kCrvN;
     for (int k = tid; k < kCrvN; k += kCrvThreads) dst[k] = crv_buf[k];
 }
@@ -203,14 +218,16 @@ __global__ void __launch_bounds__(kCrvThreads, 1) crv_ifft_mix_kernel(SigView in
                                                                        const float2 *__restrict__ Y,
                                                                        unsigned *out_peak) {
     extern __shared__ float2 crv_buf[];
+    float2 *tws = crv_buf + kCrvN;
     const int j = blockIdx.x, p = blockIdx.y, tid = threadIdx.x;
+    load_twiddles(tws, tw, tid);
     const float2 *src = Y + ((size_t)p * nblocks + j) * kCrvN;
     for (int k = tid; k < kCrvN; k += kCrvThreads) {
         const float2 v = src[k];
         crv_buf[k] = make_float2(v.x, -v.y);
     }
     __syncthreads();
-    fft16k(crv_buf, tw, tid);
+    fft16k(crv_buf, tws, tid);
     const bool has_div = in_peak != nullptr;
     const float div = has_div ? fmaxf(in_peak[p], 1e-8f) : 1.0f;
     const float mix = prm[p].mix, dry = __fsub_rn(1.0f, mix);
