@@ -171,6 +171,11 @@ STITO_API int stito_logmel(stito_handle *h, const float *x, int B, int chs, int6
 
 STITO_API int stito_get_timing(const stito_handle *h, stito_timing *out);
 
+/* Host-side setup pieces of STITO_FX_CONV_REVERB, exported for the CPU test-suite (no GPU involved): the 12 x 1023
+ * octave-band FIR bank (scipy.signal.firwin restated; out [12][1023]) and n samples of the seeded white noise. */
+STITO_API int stito_crv_host_filterbank(double sample_rate, float *out);
+STITO_API int stito_crv_host_noise(uint64_t seed, int64_t n, float *out);
+
 /* ---- native CMA-ES (host, fp64): what run_es obtains from pycma, style_transfer.py:614-673 -----------------------------
  * cma.CMAEvolutionStrategy(x0, sigma0, {"bounds": [lower, upper], "popsize": P}) -> stito_cma_create (lower >= upper: no
  * bounds); es.ask() -> stito_cma_ask (X [P][D], feasible); es.tell(X, f) -> stito_cma_tell; es.result -> stito_cma_result.

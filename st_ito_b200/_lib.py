@@ -94,6 +94,8 @@ EXPORTS = {
     "stito_embed": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "stito_logmel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),
     "stito_get_timing": (c_int, [c_void_p, POINTER(Timing)]),
+    "stito_crv_host_filterbank": (c_int, [c_double, c_void_p]),
+    "stito_crv_host_noise": (c_int, [c_uint64, c_int64, c_void_p]),
     "stito_cma_create": (c_int, [c_void_p, c_int, c_double, c_int, c_double, c_double, c_uint64, POINTER(c_void_p)]),
     "stito_cma_destroy": (None, [c_void_p]),
     "stito_cma_eig": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),

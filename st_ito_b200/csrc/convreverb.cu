@@ -316,6 +316,14 @@ void octave_filterbank(double fs, std::vector<float> &out) {
 
 }  // namespace
 
+// host-side pieces of the setup, exported through the C ABI for the CPU test-suite (tests/test_convreverb_oracle.py)
+void convreverb_host_filterbank(double sample_rate, float *out /*[12][1023]*/) {
+    std::vector<float> f;
+    octave_filterbank(sample_rate, f);
+    for (size_t i = 0; i < f.size(); ++i) out[i] = f[i];
+}
+void convreverb_host_noise(uint64_t seed, size_t count, float *out) { white_noise(seed, count, out); }
+
 void convreverb_release(ConvReverbState *s) {
     void **ptrs[] = {(void **)&s->bands, (void **)&s->twiddle, (void **)&s->H, (void **)&s->X};
     for (void **p : ptrs) {

@@ -1025,6 +1025,19 @@ int stito_logmel(stito_handle *h, const float *x, int B, int chs, int64_t L, flo
     return STITO_OK;
 }
 
+/* Host-side setup pieces of the convolution reverb, for the CPU tests: the 12 x 1023 octave-band FIR bank
+ * (scipy.signal.firwin restated) and n samples of the seeded white noise.  No GPU involved. */
+int stito_crv_host_filterbank(double sample_rate, float *out) {
+    if (!out || !(sample_rate > 36100.0)) return fail(STITO_EINVAL, "bad argument");
+    convreverb_host_filterbank(sample_rate, out);
+    return STITO_OK;
+}
+int stito_crv_host_noise(uint64_t seed, int64_t n, float *out) {
+    if (!out || n < 0) return fail(STITO_EINVAL, "bad argument");
+    convreverb_host_noise(seed, (size_t)n, out);
+    return STITO_OK;
+}
+
 int stito_get_timing(const stito_handle *hc, stito_timing *out) {
     if (!hc || !out) return fail(STITO_EINVAL, "NULL argument");
     stito_handle *h = const_cast<stito_handle *>(hc);

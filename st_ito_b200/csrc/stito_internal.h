@@ -88,6 +88,8 @@ cudaError_t convreverb_prepare(cudaStream_t st, ConvReverbState *s, double sampl
 cudaError_t launch_convreverb(cudaStream_t st, ConvReverbState *s, SigView in, const float *in_peak, float *out, int P,
                               int64_t L, const ConvRevParams *prm, unsigned *out_peak, int *launches);
 void convreverb_release(ConvReverbState *s);
+void convreverb_host_filterbank(double sample_rate, float *out);
+void convreverb_host_noise(uint64_t seed, size_t count, float *out);
 
 // ------------------------------------------------------- front-end (frontend_kernels.cu)
 struct FrontendTables {
