@@ -441,7 +441,9 @@ def run_ours(args, rank, world, local_rank):
                            f"sigma0 = 0.33, bounds [0, 1]); {gens} generations timed",
                    "l2": "per-generation working set (activations > 1 GB at 64 candidates) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": (f"population of {P_total} sharded over {world} ranks ({P_rank} candidates each), one "
-                                   f"fitness all-gather per generation") if world > 1 else "single GPU"},
+                                   f"fitness all-gather per generation: "
+                                   + ("fused into the fitness kernel over NVLink peer memory (stito_eval_population_gather)"
+                                      if ev.peer_gather else "NCCL all_gather_into_tensor")) if world > 1 else "single GPU"},
         "ms_per_generation": ms / gens,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * iters, "d2h_bytes_per_step": d2h * iters,
                 "ms_per_generation": ms_e2e / gens,

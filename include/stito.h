@@ -149,6 +149,21 @@ STITO_API int stito_set_target_embeds(stito_handle *h, const float *mid, const f
 STITO_API int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_t start,
                           int64_t len, float *fitness, float *embeds, float *audio, void *stream);
 
+/* ---- multi-GPU (one process per GPU; the population is sharded over the ranks) --------------------------------
+ * Every rank's replica of the CMA-ES needs all P fitness values each generation.  Instead of a NCCL all-gather after the
+ * fitness kernel, the fitness kernel itself stores each value into the gather buffer of EVERY rank through NVLink peer
+ * memory and publishes an epoch flag; a one-warp kernel waits for all ranks' flags.  Setup, once per handle:
+ *   stito_gather_export(h, capacity >= P_total, handle[64])   -> a cudaIpcMemHandle_t of this rank's gather block;
+ *   (exchange the 64-byte handles between the ranks, e.g. torch.distributed.all_gather_object)
+ *   stito_gather_attach(h, rank, world, handles[world][64])    -> opens the peers' blocks (world <= 16, same node).
+ * Per generation: stito_eval_population_gather scores the shard W [P_local][D] = candidates [lo, lo + P_local) of a population
+ * of P_total and returns ALL P_total fitness values (host or device pointer).  Collective: every rank must call it once per
+ * generation (P_local may be 0); a rank that never arrives makes the others fail after a bounded wait (20 s). */
+STITO_API int stito_gather_export(stito_handle *h, int capacity, void *ipc_handle_out);
+STITO_API int stito_gather_attach(stito_handle *h, int rank, int world, const void *ipc_handles);
+STITO_API int stito_eval_population_gather(stito_handle *h, const double *W, int P_local, int D, int64_t start, int64_t len,
+                                           int lo, int P_total, float *fitness_all, void *stream);
+
 /* process_audio (style_transfer.py:45-115) for P parameter vectors on an arbitrary signal:
  * x[chs, L] -> y[P, out_chs, L].  final_normalize=1 applies the closing peak normalisation
  * (style_transfer.py:113); 0 returns the raw chain output (what plugin.process returns). */

@@ -9,10 +9,11 @@ nvidia-smi --query-gpu=index,name --format=csv,noheader > gpurun_out/${TAG}_n${N
 run --steps 4 --warmup 2 --no-cpu-baseline
 run --config 3 --iters 10 --steps 3 --warmup 1 --no-cpu-baseline
 run --weak --steps 2 --warmup 1 --iters 10 --no-cpu-baseline
+STITO_PEER_GATHER=0 run --steps 4 --warmup 2 --no-cpu-baseline
 python - <<PY
 import json
 for ln in open('gpurun_out/${TAG}_n${N}.jsonl'):
     d=json.loads(ln); r=d['roofline']
-    print(d['metric'], d['scaling'], 'n_gpus', d['n_gpus'], 'value %.0f e2e %.0f ms/gen %.3f'%(d['value'], d['e2e']['value'], d['ms_per_generation']), {k:round(v,3) for k,v in r['stages_ms_per_generation'].items()}, 'cma %.3f'%d['host_cma_ms_per_generation'], d.get('shard_check'))
+    print(d['config']['parallelism'][-60:], '|', d['metric'], d['scaling'], 'n_gpus', d['n_gpus'], 'value %.0f e2e %.0f ms/gen %.3f'%(d['value'], d['e2e']['value'], d['ms_per_generation']), {k:round(v,3) for k,v in r['stages_ms_per_generation'].items()}, 'cma %.3f'%d['host_cma_ms_per_generation'], d.get('shard_check'))
 PY
 tail -5 gpurun_out/${TAG}_n${N}.err

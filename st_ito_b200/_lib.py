@@ -88,6 +88,10 @@ EXPORTS = {
     "stito_set_target_embeds": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "stito_eval_population": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
+    "stito_gather_export": (c_int, [c_void_p, c_int, c_void_p]),
+    "stito_gather_attach": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "stito_eval_population_gather": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_int, c_void_p,
+                                             c_void_p]),
     "stito_process": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_void_p,
                               c_void_p]),
     "stito_out_channels": (c_int, [c_void_p, c_int]),

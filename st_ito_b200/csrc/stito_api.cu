@@ -191,6 +191,13 @@ struct stito_handle {
     int comp_fallbacks_total = 0;
     ReverbGeom rgeom{};
     ConvReverbState crv;
+    // multi-GPU fitness exchange over peer memory (stito_gather_*)
+    void *gather_block = nullptr;          // exported: [2][capacity] floats + [2][kGatherMaxWorld] ints
+    int gather_capacity = 0, gather_epoch = 0;
+    bool gather_attached = false;
+    GatherPeers gather_peers{};
+    void *gather_opened[kGatherMaxWorld] = {};
+    int *gather_done = nullptr;
     TcWorkspace tcws;
 
     // timing
@@ -692,6 +699,10 @@ void stito_destroy(stito_handle *h) {
     h->hflags.release();
     tc_workspace_release(&h->tcws);
     convreverb_release(&h->crv);
+    for (int r = 0; r < kGatherMaxWorld; ++r)
+        if (h->gather_opened[r]) cudaIpcCloseMemHandle(h->gather_opened[r]);
+    if (h->gather_block) cudaFree(h->gather_block);
+    if (h->gather_done) cudaFree(h->gather_done);
     for (int i = 0; i < kNumEvents; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 13; ++i) if (h->ev_conv[i]) cudaEventDestroy(h->ev_conv[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -896,6 +907,105 @@ int stito_eval_population(stito_handle *h, const double *W, int P, int D, int64_
     t.frontend_bytes = P * (4.0 * ochs * len + (double)ochs * T * h->n_mels * 4.0);
     h->timing_pending = true;
     h->timing_scale = (double)P / (P < h->microbatch ? P : h->microbatch);  // stage times are measured on the first micro-batch
+    return STITO_OK;
+}
+
+/* ---- multi-GPU: fitness all-gather over NVLink peer memory, fused into the fitness kernel (fitness.cu) ---- */
+int stito_gather_export(stito_handle *h, int capacity, void *ipc_handle_out) {
+    if (!h || !ipc_handle_out || capacity <= 0) return fail(STITO_EINVAL, "bad argument");
+    CU(cudaSetDevice(h->device));
+    if (h->gather_block) return fail(STITO_ESTATE, "gather block already exported");
+    const size_t bytes = (size_t)2 * capacity * sizeof(float) + (size_t)2 * kGatherMaxWorld * sizeof(int);
+    CU(cudaMalloc(&h->gather_block, bytes));
+    CU(cudaMemset(h->gather_block, 0, bytes));
+    CU(cudaMalloc((void **)&h->gather_done, sizeof(int)));
+    CU(cudaMemset(h->gather_done, 0, sizeof(int)));
+    CU(cudaDeviceSynchronize());
+    h->gather_capacity = capacity;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, h->gather_block));
+    memcpy(ipc_handle_out, &hd, sizeof(hd));
+    return STITO_OK;
+}
+
+int stito_gather_attach(stito_handle *h, int rank, int world, const void *ipc_handles) {
+    if (!h || !ipc_handles) return fail(STITO_EINVAL, "NULL argument");
+    if (!h->gather_block) return fail(STITO_ESTATE, "stito_gather_export has not been called");
+    if (world < 1 || world > kGatherMaxWorld || rank < 0 || rank >= world) return fail(STITO_EINVAL, "rank %d / world %d out of range (max %d ranks)", rank, world, kGatherMaxWorld);
+    CU(cudaSetDevice(h->device));
+    GatherPeers &g = h->gather_peers;
+    g.world = world; g.rank = rank; g.capacity = h->gather_capacity;
+    for (int r = 0; r < world; ++r) {
+        void *base = h->gather_block;
+        if (r != rank) {
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, (const char *)ipc_handles + (size_t)r * sizeof(hd), sizeof(hd));
+            CU(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+            h->gather_opened[r] = base;
+        }
+        g.buf[r] = reinterpret_cast<float *>(base);
+        g.flag[r] = reinterpret_cast<int *>(reinterpret_cast<char *>(base) + (size_t)2 * g.capacity * sizeof(float));
+    }
+    h->gather_attached = true;
+    h->gather_epoch = 0;
+    return STITO_OK;
+}
+
+int stito_eval_population_gather(stito_handle *h, const double *W, int P_local, int D, int64_t start, int64_t len, int lo,
+                                 int P_total, float *fitness_all, void *stream) {
+    if (!h || (!W && P_local > 0) || !fitness_all) return fail(STITO_EINVAL, "NULL argument");
+    if (!h->gather_attached) return fail(STITO_ESTATE, "stito_gather_attach has not been called");
+    if (P_local < 0 || lo < 0 || lo + P_local > P_total || P_total > h->gather_capacity)
+        return fail(STITO_EINVAL, "shard [%d, %d) of a population of %d does not fit (capacity %d)", lo, lo + P_local, P_total, h->gather_capacity);
+    if (D != h->chain.num_w) return fail(STITO_EINVAL, "parameter vectors have %d entries, chain expects %d", D, h->chain.num_w);
+    if (h->in_chs == 0) return fail(STITO_ESTATE, "stito_set_input has not been called");
+    if (!h->has_encoder) return fail(STITO_ESTATE, "handle was created without encoder weights");
+    if (!h->has_target) return fail(STITO_ESTATE, "no target set (stito_set_target / stito_set_target_embeds)");
+    if (start < 0 || len <= 0 || start + len > h->in_cap) return fail(STITO_EINVAL, "view outside the padded input");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->own_stream;
+    const int E = h->embed_dim;
+    int launches = 0, overflowed = 0, comp_fallbacks = 0;
+    if (P_local > 0) {
+        const double *Wh = nullptr;
+        int rc = fetch_W(h, W, P_local, D, st, &Wh);
+        if (rc) return rc;
+        // phase 1: embeddings of my shard (redone if the activation scales had to be re-calibrated); nothing is published yet
+        for (;;) {
+            rc = enqueue_population(h, st, Wh, P_local, D, start, len, nullptr, nullptr, nullptr, &launches);
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(st));
+            comp_fallbacks = h->hflags.as<int>()[3];
+            if (!tc_after_pass(h)) break;
+            ++overflowed;
+        }
+    }
+    // phase 2: fitness of my shard, stored straight into every rank's gather buffer; wait for everybody's; read the vector
+    const int epoch = ++h->gather_epoch, parity = epoch & 1;
+    const float *mid_all = h->emb.as<float>(), *side_all = mid_all + (size_t)P_local * E;
+    GatherPeers &g = h->gather_peers;
+    CU(launch_fitness_gather(st, mid_all, side_all, h->target.as<float>(), h->target.as<float>() + E, P_local, E, lo, g, parity,
+                             epoch, h->gather_done, g.flag[g.rank], &launches));
+    CU(cudaMemcpyAsync(fitness_all, g.buf[g.rank] + (size_t)parity * g.capacity, (size_t)P_total * sizeof(float), cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+    h->comp_fallbacks_total += comp_fallbacks;
+    stito_timing &t = h->timing;
+    const bool had_pass = P_local > 0;
+    memset(&t, 0, sizeof(t));
+    t.launches = launches;
+    t.precision = h->precision;
+    t.comp_fallbacks = comp_fallbacks;
+    t.act_overflow = overflowed;
+    if (had_pass) {
+        const int chs = h->in_chs, ochs = out_channels(h->chain, chs);
+        const int T = (int)(len / h->hop) + 1;
+        t.encoder_flop = encoder_flops(P_local * ochs, T, h->n_mels);
+        t.dsp_bytes = 4.0 * chs * len + 4.0 * ochs * len * P_local;
+        t.frontend_bytes = P_local * (4.0 * ochs * len + (double)ochs * T * h->n_mels * 4.0);
+        h->timing_scale = (double)P_local / (P_local < h->microbatch ? P_local : h->microbatch);
+    }
+    h->timing_pending = had_pass;
     return STITO_OK;
 }
 

@@ -148,4 +148,16 @@ cudaError_t launch_embed_normalize(cudaStream_t st, float *mid, float *side, int
 cudaError_t launch_fitness(cudaStream_t st, const float *mid, const float *side, const float *tgt_mid,
                            const float *tgt_side, int B, int E, float *fitness, int *launches);
 
+// fitness + all-gather over peer memory (multi-GPU).  buf[r] / flag[r] point into rank r's exported gather block:
+// [2][capacity] floats followed by [2][kGatherMaxWorld] ints.
+constexpr int kGatherMaxWorld = 16;
+struct GatherPeers {
+    float *buf[kGatherMaxWorld];
+    int *flag[kGatherMaxWorld];
+    int world, rank, capacity;
+};
+cudaError_t launch_fitness_gather(cudaStream_t st, const float *mid, const float *side, const float *tgt_mid,
+                                  const float *tgt_side, int n_local, int E, int lo, const GatherPeers &peers, int parity,
+                                  int epoch, int *done_counter, const int *local_flags, int *launches);
+
 }  // namespace stito

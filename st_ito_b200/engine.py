@@ -263,6 +263,47 @@ class Engine:
             return fit, emb, aud
         return fit.clone(), (emb.clone() if emb is not None else None), aud
 
+    # -- multi-GPU: fitness all-gather over peer memory, fused into the fitness kernel ---------------
+    def gather_setup(self, rank: int, world: int, capacity: int = 4096) -> bool:
+        """Export this handle's gather block, exchange the CUDA IPC handles over torch.distributed and attach the peers'
+        blocks (stito_gather_export / _attach).  Collective.  Returns False (on every rank) if any rank could not set it
+        up -- e.g. peer access between the GPUs is not available -- in which case callers keep the NCCL all-gather."""
+        import ctypes
+
+        import torch.distributed as dist
+
+        ok, mine = 1, bytes(64)
+        try:
+            buf = ctypes.create_string_buffer(64)
+            check(_lib.lib().stito_gather_export(self._h, int(capacity), buf))
+            mine = buf.raw
+        except Exception:
+            ok = 0
+        handles = [None] * world
+        dist.all_gather_object(handles, (ok, mine))
+        if all(h[0] for h in handles):
+            try:
+                blob = b"".join(h[1] for h in handles)
+                check(_lib.lib().stito_gather_attach(self._h, int(rank), int(world), blob))
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        flags = [None] * world
+        dist.all_gather_object(flags, ok)
+        self._gather_ready = all(flags)
+        return self._gather_ready
+
+    def eval_population_gather(self, W, start: int, length: int, lo: int, P_total: int):
+        """Score the shard W = candidates [lo, lo + len(W)) of a population of P_total and return ALL P_total fitness values
+        (pinned host tensor): stito_eval_population_gather.  Collective over the ranks of gather_setup()."""
+        W = np.ascontiguousarray(np.asarray(W, dtype=np.float64))
+        P, D = (W.shape if W.ndim == 2 else (0, 0))
+        fit = self._pinned("fit_all", (int(P_total),))
+        check(_lib.lib().stito_eval_population_gather(self._h, ptr(W) if P > 0 else None, int(P), int(D), int(start), int(length),
+                                                      int(lo), int(P_total), ptr(fit), _stream_ptr(self.device)))
+        return fit.clone()
+
     def _pinned(self, key, shape):
         cache = self.__dict__.setdefault("_pinned_cache", {})
         k = (key, tuple(shape))

@@ -225,6 +225,12 @@ class FusedEvaluator:
         x = input_audio[0] if input_audio.dim() == 3 else input_audio
         self.in_chs, self.x_len = int(x.shape[0]), int(x.shape[-1])
         engine.set_input(x, min_len=self.crop_len)
+        # multi-GPU: the per-generation fitness all-gather runs over NVLink peer memory, fused into the fitness kernel
+        # (stito_eval_population_gather); NCCL stays as the fall-back (and for embeddings / audio, which are not hot)
+        self.peer_gather = False
+        if self.world_size > 1 and sdist.backend() == "nccl" and os.environ.get("STITO_PEER_GATHER", "1") != "0":
+            ready = getattr(engine, "_gather_ready", None)
+            self.peer_gather = ready if ready is not None else engine.gather_setup(self.rank, self.world_size)
 
     def view_for(self, x_len: int, parallel: bool):
         """Length policy of evaluate (reference :499-518): (start, length) into the padded input."""
@@ -254,6 +260,9 @@ class FusedEvaluator:
             # rank r scores the slice [lo, hi) -- possibly empty when there are more ranks than candidates -- and
             # the rows are all-gathered; on NCCL the results stay on the GPU until after the collective
             lo, hi, _ = sdist.shard_bounds(P, self.world_size, self.rank)
+            if self.peer_gather and not want_embeds and not want_audio and P <= 4096:
+                fit = self.engine.eval_population_gather(W[lo:hi], start, length, lo, P)
+                return fit.tolist(), None, None
             on_gpu = sdist.backend() == "nccl"
             fit, emb, aud = self.engine.eval_population(W[lo:hi], start, length, want_embeds=want_embeds,
                                                         want_audio=want_audio, in_chs=self.in_chs,
