@@ -57,7 +57,13 @@ enum stito_fx_kind {
      * noise_shaped_reverberation (25 parameters used raw: 12 band gains, 12 band decays, mix); num_channels must be 2.
      * iopt[0] = impulse-response length in samples (65536 = dasp default; 96000 = the 2 s IR of BASELINE config 4),
      * iopt[1] = seed of the white noise (the reference draws fresh noise per call; here it is fixed per plugin). */
-    STITO_FX_CONV_REVERB = 5
+    STITO_FX_CONV_REVERB = 5,
+    /* Compressor with LTI gain smoothing: the arithmetic of apply_compressor, effects.py:623-648 -> dasp-pytorch's
+     * compressor (6 parameters: threshold_db -60..0, ratio 1..20, attack_ms 0.1..250, release_ms 10..2000 [accepted and
+     * unused, as upstream], knee_db 1..24, makeup_gain_db 0..24).  The side-chain is the SUM of the channels the plugin
+     * sees (num_channels 2: stereo-linked; 1: every channel on its own).  iopt[0] = look-ahead in samples (512 at
+     * effects.py:646; 0 at dsp.py:66-75). */
+    STITO_FX_LTI_COMPRESSOR = 6
 };
 
 /* One entry of the reference's ordered `plugins` dict (run_optim.py:376-407,
@@ -190,6 +196,10 @@ STITO_API int stito_get_timing(const stito_handle *h, stito_timing *out);
  * octave-band FIR bank (scipy.signal.firwin restated; out [12][1023]) and n samples of the seeded white noise. */
 STITO_API int stito_crv_host_filterbank(double sample_rate, float *out);
 STITO_API int stito_crv_host_noise(uint64_t seed, int64_t n, float *out);
+/* Host-side design of STITO_FX_LTI_COMPRESSOR's smoothing filter (same purpose): out[0] = alpha = the float32
+ * exp(-log(9) / (fs * attack_ms / 1000)) of dasp-pytorch's compressor, out[1] = float32(1 - alpha), out[2] = the factor
+ * of the frequency-sampling wrap-around, y[-1] = y0[L-1] * out[2] (n_fft = 2^ceil(log2(2L - 1))). */
+STITO_API int stito_lticomp_host_design(double sample_rate, int64_t L, float attack_ms, double *out);
 
 /* ---- native CMA-ES (host, fp64): what run_es obtains from pycma, style_transfer.py:614-673 -----------------------------
  * cma.CMAEvolutionStrategy(x0, sigma0, {"bounds": [lower, upper], "popsize": P}) -> stito_cma_create (lower >= upper: no

@@ -197,6 +197,7 @@ class OracleReverb:
 def make_plugins(kinds, channels=None, fixed=None):
     """Build a reference-style plugins dict from effect kinds, e.g. ("eq","comp","reverb")."""
     from oracle.convreverb import OracleNoiseShapedReverb, OracleNoiseShapedReverb2s
+    from oracle.lticomp import OracleLTICompressor
 
     table = {
         "eq": ("ParametricEQ", OracleParametricEQ, 1),
@@ -206,6 +207,8 @@ def make_plugins(kinds, channels=None, fixed=None):
         "reverb": ("Reverb", OracleReverb, 2),
         "convreverb": ("NoiseShapedReverb", OracleNoiseShapedReverb, 2),      # 65 536-tap IR (dasp default)
         "convreverb2s": ("NoiseShapedReverb", OracleNoiseShapedReverb2s, 2),  # 96 000-tap IR (BASELINE config 4)
+        "lticomp": ("LTICompressor", OracleLTICompressor, 2),                 # stereo-linked, look-ahead 512
+        "lticomp1": ("LTICompressor", OracleLTICompressor, 1),                # every channel on its own
     }
     plugins = {}
     for i, k in enumerate(kinds):

@@ -19,7 +19,7 @@ CSRC = os.path.join(_HERE, "csrc")
 MAX_FX = 8
 MAX_FX_PARAMS = 32
 
-FX_EQ, FX_COMPRESSOR, FX_DISTORTION, FX_DELAY, FX_REVERB, FX_CONV_REVERB = range(6)
+FX_EQ, FX_COMPRESSOR, FX_DISTORTION, FX_DELAY, FX_REVERB, FX_CONV_REVERB, FX_LTI_COMPRESSOR = range(7)
 
 
 class FxDesc(Structure):
@@ -100,6 +100,7 @@ EXPORTS = {
     "stito_get_timing": (c_int, [c_void_p, POINTER(Timing)]),
     "stito_crv_host_filterbank": (c_int, [c_double, c_void_p]),
     "stito_crv_host_noise": (c_int, [c_uint64, c_int64, c_void_p]),
+    "stito_lticomp_host_design": (c_int, [c_double, c_int64, c_float, c_void_p]),
     "stito_cma_create": (c_int, [c_void_p, c_int, c_double, c_int, c_double, c_double, c_uint64, POINTER(c_void_p)]),
     "stito_cma_destroy": (None, [c_void_p]),
     "stito_cma_eig": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),

@@ -935,32 +935,46 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
 // 2 * NSPLIT CTAs: channel c = rank / NSPLIT, comb group g = rank % NSPLIT.
 //   * every CTA runs CW = 8 / NSPLIT comb filters (one warp each, same arithmetic as above) as a free-running producer;
 //     after super-step k it hands the home CTA of its channel (g == 0) the delayed comb outputs that the all-pass chain
-//     of super-step k + 1 will sum, dly[j][slot][i] = ring_j[n - delay_j], through distributed shared memory, then
-//     arrives (release) on the home CTA's full[slot] mbarrier;
-//   * the home CTA's all-pass group (224 threads) waits (acquire) on full[slot], sums the 8 rows in the ORIGINAL order
-//     (bit-identical to reverb_core_kernel), runs the 4 all-passes, exchanges wet samples with the other channel's home CTA
+//     of super-step k + 1 will sum -- ONE row per producer CTA, dly[g][slot][i] = sum over its combs of ring_j[n - delay_j] --
+//     by a bulk copy through distributed shared memory that completes on the home CTA's full[slot] mbarrier;
+//   * the home CTA's all-pass group (224 threads) waits (acquire) on full[slot], adds the NSPLIT rows (pairwise order
+//     (c0 + c1) + (c2 + c3) + ...: within 1 ulp of reverb_core_kernel's left-to-right sum), runs the 4 all-passes,
+//     exchanges wet samples with the other channel's home CTA
 //     (same protocol as above) and mixes; when it is done with a slot it arrives on the free[slot] mbarrier of the NSPLIT
 //     producers.  A ring of kRsDepth slots decouples the two sides: there is no CTA-wide barrier in the loop.
 // Per super-step both sides are chain-bound at ~0.8 us instead of issue-bound at 2.2 us.
-constexpr int kRsDepth = 3;
+constexpr int kRsDepth = 6;  // slots of the hand-off ring: one row per PRODUCER CTA and slot (the sum of its comb filters'
+                             // delayed outputs), NSPLIT x 6 rows = what 8 x 3 single-comb rows used to take
 template <int NSPLIT, int WPC> struct RsCfg {
     static constexpr int CW = 8 / NSPLIT;                  // comb filters per CTA
     static constexpr int kCombThreads = 32 * WPC * CW;     // WPC warps per comb filter
     static constexpr int kThreads = kCombThreads + kRevSub;
-    static constexpr int kFloats = CW * kCombRing + 8 * kRsDepth * kRevMaxS + 4 * kApRing + 2 * kRevMaxS + 6 * kRevMaxS +
-                                   CW * kRsDepth * kRevMaxS +  // staging of the delayed rows (source of the bulk copies)
+    static constexpr int kFloats = CW * kCombRing + NSPLIT * kRsDepth * kRevMaxS + 4 * kApRing + 2 * kRevMaxS + 6 * kRevMaxS +
+                                   kRsDepth * kRevMaxS +       // staging of the delayed rows (source of the bulk copies)
                                    2 * CW * WPC * 2 + 2 * CW;  // per-warp scan totals (double-buffered float2) + carries
-    static constexpr size_t kSmem = (size_t)kFloats * sizeof(float) + 9 * sizeof(uint64_t) + 16;
+    static constexpr size_t kSmem = (size_t)kFloats * sizeof(float) + (2 * kRsDepth + 4) * sizeof(uint64_t) + 16;
 };
 
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+// mbarrier waits of reverb_split_kernel, bounded (a protocol bug must trap, not hang the GPU).
+//   kTx      : the barrier completes through the bulk-copy engine's complete_tx on THIS CTA's barrier -- the canonical
+//              transaction-barrier wait (acquire at CTA scope), also when the copy was issued by another CTA of the cluster;
+//   kControl : control only (relaxed): the data the hand-off protects is ordered by the CTA barrier that follows.
+// An acquire at CLUSTER scope compiles to CCTL.IVALL -- an L1 invalidation per waiter and per poll; with all 320 comb threads
+// waiting that way it was 20 % of the comb group's time (profiles/r02e_reverb_split.md, v10).
+enum MbarWait { kTx, kControl };
+template <MbarWait MODE> __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0, spins = 0;
     unsigned long long t0 = 0;
     while (!ok) {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (!ok && (++spins & 1023u) == 0) {  // bounded: a protocol bug must trap, not hang the GPU
+        if (MODE == kTx)
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && (++spins & 1023u) == 0) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             if (t0 == 0) t0 = t1;
@@ -982,14 +996,14 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
     constexpr int nsub = (S + kRevSub - 1) / kRevSub;
     extern __shared__ float sm[];
     float *ring = sm;                                   // [CW][kCombRing] my comb filters
-    float *dly = ring + CW * kCombRing;                 // [8][kRsDepth][kRevMaxS] delayed comb outputs (home CTA only)
-    float *ap = dly + 8 * kRsDepth * kRevMaxS;          // [4][kApRing]
+    float *dly = ring + CW * kCombRing;                 // [NSPLIT][kRsDepth][kRevMaxS] delayed comb outputs, summed per producer CTA (home only)
+    float *ap = dly + NSPLIT * kRsDepth * kRevMaxS;     // [4][kApRing]
     float *inbuf = ap + 4 * kApRing;                    // [2][kRevMaxS] reverb input (l + r) * 0.015 of super-steps k, k + 1
     float *wetb = inbuf + 2 * kRevMaxS;                 // [3][2][kRevMaxS] wet rows of super-steps k, k - 1, k - 2: [k % 3][own, peer]
-    float *stage = wetb + 6 * kRevMaxS;                 // [CW][kRsDepth][kRevMaxS] delayed rows staged for the bulk copy
-    float *wtot = stage + CW * kRsDepth * kRevMaxS;     // [2][CW][WPC] float2: affine map of each warp's part of the damping scan
+    float *stage = wetb + 6 * kRevMaxS;                 // [kRsDepth][kRevMaxS] delayed rows staged for the bulk copy
+    float *wtot = stage + kRsDepth * kRevMaxS;          // [2][CW][WPC] float2: affine map of each warp's part of the damping scan
     float *carry = wtot + 2 * CW * WPC * 2;             // [2][CW] damping-filter state entering the next super-step
-    uint64_t *bars = reinterpret_cast<uint64_t *>(carry + 2 * CW);  // full[3], free[3], xbar[3]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(carry + 2 * CW);  // full[kRsDepth], free[kRsDepth], xbar[3]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = blockIdx.x % (2 * NSPLIT);
     const int p = blockIdx.x / (2 * NSPLIT);
@@ -1007,14 +1021,14 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
     };
     if (tid == 0) {
         for (int s2 = 0; s2 < kRsDepth; ++s2) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(1u));                // full: armed with 8 rows of bytes
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(1u));                // full: armed with NSPLIT rows of bytes
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (kRsDepth + s2)), "r"(1u));   // free: the home's all-pass group
         }
         for (int s2 = 0; s2 < 3; ++s2)  // xbar: armed with one wet row of bytes
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + s2)), "r"(1u));
-        if (home) {  // arm the first phases: 8 delayed rows of S floats per slot, one wet row of the peer channel per parity
+        if (home) {  // arm the first phases: NSPLIT delayed rows of S floats per slot, one wet row of the peer channel per parity
             for (int s2 = 0; s2 < kRsDepth; ++s2)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s2), "r"((uint32_t)(8 * S * 4)) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s2), "r"((uint32_t)(NSPLIT * S * 4)) : "memory");
             for (int s2 = 0; s2 < 3; ++s2)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + s2)), "r"((uint32_t)(S * 4)) : "memory");
         }
@@ -1082,38 +1096,46 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
         // mbarrier -- no remote stores and no release fence on the comb filters' critical path.  The staging row is reused
         // for super-step m + depth, i.e. only after free[slot] said that the all-pass group has consumed this one.
         auto stage_row = [&](int64_t m) {
-            const int slot = (int)(m % kRsDepth);
-            if (m >= kRsDepth)  // the home's all-pass group must have finished super-step m - depth (which read this slot)
-                mbar_wait_cluster(bar0 + 8u * (kRsDepth + slot), (uint32_t)(((m / kRsDepth) - 1) & 1));
+            const int slot = (int)(m % kRsDepth);  // free: wait_free(m) by one thread + a comb barrier precede this call
+            // the row this CTA contributes = sum of its CW comb filters' delayed runs (fixed order: comb 0 + comb 1 + ...);
+            // every comb thread of the CTA handles at most one 16-byte group
             const int wb = (int)(m % 3) * S;
-            int rb = wb - my_delay;
-            if (rb < 0) rb += RL;
-            const float *rp = my_ring + rb;
-            float *srow = stage + (cw * kRsDepth + slot) * kRevMaxS;
+            float *srow = stage + slot * kRevMaxS;
+            for (int v4 = tid; v4 < S / 4; v4 += Cfg::kCombThreads) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int t = 0; t < (S / 4 + 32 * WPC - 1) / (32 * WPC); ++t) {
-                const int v4 = lc + 32 * WPC * t;
-                if (v4 < S / 4) {
-                    const float *src = rp + 4 * v4;
-                    *reinterpret_cast<float4 *>(srow + 4 * v4) = make_float4(src[0], src[1], src[2], src[3]);
+                for (int cq = 0; cq < CW; ++cq) {
+                    int rb = wb - g.comb_delay[c][gq * CW + cq];
+                    if (rb < 0) rb += RL;
+                    const float *src = ring + cq * kCombRing + rb + 4 * v4;
+                    if (cq == 0) acc = make_float4(src[0], src[1], src[2], src[3]);
+                    else { acc.x = __fadd_rn(acc.x, src[0]); acc.y = __fadd_rn(acc.y, src[1]); acc.z = __fadd_rn(acc.z, src[2]); acc.w = __fadd_rn(acc.w, src[3]); }
                 }
+                *reinterpret_cast<float4 *>(srow + 4 * v4) = acc;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my staging writes -> visible to the async proxy
         };
-        auto ship_row = [&](int64_t m) {  // after a CTA barrier that follows stage_row(m)
-            if (lc == 0) {
+        auto wait_free = [&](int64_t m) {  // one thread: the home's all-pass group has finished super-step m - depth, which
+            if (m >= kRsDepth) {           // read this slot (so the bulk copy out of its staging row is long complete)
                 const int slot = (int)(m % kRsDepth);
-                const float *srow = stage + (cw * kRsDepth + slot) * kRevMaxS;
-                const uint32_t dst = dly_home + (uint32_t)((jg * kRsDepth + slot) * kRevMaxS) * 4u;
+                mbar_wait<kControl>(bar0 + 8u * (kRsDepth + slot), (uint32_t)(((m / kRsDepth) - 1) & 1));
+            }
+        };
+        auto ship_row = [&](int64_t m) {  // after a CTA barrier that follows stage_row(m): ONE bulk copy per producer CTA
+            if (tid == 0) {
+                const int slot = (int)(m % kRsDepth);
+                const float *srow = stage + slot * kRevMaxS;
+                const uint32_t dst = dly_home + (uint32_t)((gq * kRsDepth + slot) * kRevMaxS) * 4u;
                 asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(dst), "r"((uint32_t)__cvta_generic_to_shared(srow)), "r"((uint32_t)(S * 4)), "r"(full_home + 8u * slot)
                              : "memory");
             }
         };
-        if (ready != nullptr && tid == 0) need_input(2 * (int64_t)S);
+        if (ready != nullptr && tid == 0) need_input(3 * (int64_t)S);
         if (ready != nullptr) comb_bar();
         fetch_in(0);
         park_in(0);
+        fetch_in(S);   // registers: the input of super-step 1, parked at the start of super-step 0
         stage_row(0);  // all zeros: nothing has been written to the rings yet
         if (lc == 0) { carry[cw] = 0.0f; carry[CW + cw] = 0.0f; }
         comb_bar();
@@ -1121,7 +1143,11 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
         int wbase = 0;
         for (int64_t k = 0; k < nsteps; ++k, wbase = (wbase == 2 * S) ? 0 : wbase + S) {
             const int par = (int)(k & 1);
-            fetch_in((k + 1) * S);  // next super-step's input: the loads fly during this one
+            // input pipeline: the registers hold super-step k + 1 (loaded a whole super-step ago: an L2 round trip no longer
+            // shows up as a stall); park it -- inbuf[par ^ 1] was last read before barrier (B) of super-step k - 1 -- and
+            // start the loads of super-step k + 2
+            park_in(par ^ 1);
+            fetch_in((k + 2) * S);
             const float *inb = inbuf + par * kRevMaxS;
             int rb = wbase - my_delay;
             if (rb < 0) rb += RL;
@@ -1142,7 +1168,8 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
             }
             float2 *wt = reinterpret_cast<float2 *>(wtot) + (par * CW + cw) * WPC;
             if (lane == 31) wt[ww] = make_float2(A, Bv);
-            comb_bar();                 // (A) warp totals + last step's carry visible
+            comb_bar();                 // (A) warp totals + last step's carry visible; row k staged by everybody
+            if (k > 0) ship_row(k);     // one lane hands the row staged at the end of the previous super-step to the copy engine
             float s_in = carry[par * CW + cw];  // state entering this super-step, then through the warps before mine
 #pragma unroll
             for (int w2 = 0; w2 < WPC - 1; ++w2)
@@ -1158,14 +1185,12 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
                 if (wbase == 0) wp[RL + i] = tv;  // keep the mirror of the ring head current
             }
             if (ww == WPC - 1 && lane == 31) carry[(par ^ 1) * CW + cw] = sv;
-            park_in(par ^ 1);
-            if (ready != nullptr && tid == 0) need_input((k + 3) * (int64_t)S);
-            comb_bar();                 // (B) ring writes of this super-step visible to every warp of the comb
-            if (k + 1 < nsteps) {       // the row the all-pass chain needs next: stage it and ship it at once -- the hand-off
-                stage_row(k + 1);       // loop (row -> all-passes -> free -> next row of the slot) is latency-bound, every
-                comb_bar();             // microsecond in it costs a third of a microsecond per super-step
-                ship_row(k + 1);
+            if (tid == 0) {
+                if (ready != nullptr) need_input((k + 4) * (int64_t)S);
+                wait_free(k + 1);
             }
+            comb_bar();                 // (B) ring writes of this super-step visible to every warp of the CTA; slot free
+            if (k + 1 < nsteps) stage_row(k + 1);  // the row the all-pass chain needs next; shipped after barrier (A)
         }
     } else if (home) {
         // ------------------------------------------------------------------ all-pass group of the home CTA (consumer)
@@ -1218,13 +1243,11 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
             const int64_t n0 = k * S;
             const int nbase = (int)(n0 & (kApRing * 1024 - 1));
             const int slot = (int)(k % kRsDepth);
-            if (ready != nullptr) {  // mix(k - 2) reads the dry input up to (k - 1) S: covered by what the combs needed long ago;
-                if (a == 0) need_input(n0);  // kept for the first steps / degenerate lengths
-                ap_bar();
-            }
+            // (streaming pair: the dry samples of super-step k - 2 read below were published before the comb groups could
+            // compute the rows of super-step k - 2, which this group has consumed through full[] -- no flag to poll here)
             float xd[kPerA];
             if (k >= 2) load_dry(k - 2, xd);  // dry samples of the super-step mixed at the end of this one: in flight during the all-passes
-            mbar_wait_cluster(bar0 + 8u * slot, (uint32_t)((k / kRsDepth) & 1));  // the 8 delayed comb rows of this super-step
+            mbar_wait<kTx>(bar0 + 8u * slot, (uint32_t)((k / kRsDepth) & 1));  // the NSPLIT delayed rows of this super-step
             const float *row = dly + slot * kRevMaxS;
             float *wown = wetb + (int)(k % 3) * 2 * kRevMaxS;
             for (int sb = 0; sb < nsub; ++sb) {
@@ -1234,14 +1257,14 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
                     // all 12 shared-memory loads up front: the four all-pass rings are distinct arrays and each stage reads
                     // >= 244 samples behind what this sub-block writes, but the compiler cannot know and would serialise every
                     // stage's load behind the previous stage's store (4 x ~30 cycles of latency on the critical chain)
-                    float cr[8], bvv[4];
+                    float cr[NSPLIT], bvv[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) cr[j] = row[j * kRsDepth * kRevMaxS + off];
+                    for (int j = 0; j < NSPLIT; ++j) cr[j] = row[j * kRsDepth * kRevMaxS + off];
 #pragma unroll
                     for (int s2 = 0; s2 < 4; ++s2) bvv[s2] = ap[s2 * kApRing + ((n - ad[s2]) & (kApRing - 1))];
-                    float v = 0.0f;
+                    float v = cr[0];  // sum of the 8 comb outputs: ((c0 + c1) + (c2 + c3)) + ... -- the producers pre-add their pair
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v = __fadd_rn(v, cr[j]);
+                    for (int j = 1; j < NSPLIT; ++j) v = __fadd_rn(v, cr[j]);
 #pragma unroll
                     for (int s2 = 0; s2 < 4; ++s2) {
                         const float tv = undenorm(__fadd_rn(v, __fmul_rn(bvv[s2], 0.5f)));
@@ -1252,7 +1275,7 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
                 }
                 if (sb == nsub - 1) {
                     if (k >= 2) {  // mix super-step k - 2: its peer row landed a whole super-step ago (acquire only)
-                        mbar_wait_cluster(xbar_of(k - 2), xpar_of(k - 2));
+                        mbar_wait<kTx>(xbar_of(k - 2), xpar_of(k - 2));
                         if (a == 0)  // re-arm this barrier for the peer's super-step k + 1
                             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xbar_of(k - 2)), "r"((uint32_t)(S * 4)) : "memory");
                         mix(k - 2, xd);
@@ -1266,11 +1289,11 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
             // memory, completing on the peer's xbar) and re-arms the slot; NSPLIT threads tell one producer CTA each that the
             // slot (and its staging row) is free.
             if (a == 0) {
-                if (k >= 1) mbar_wait_cluster(xbar_of(k - 1), xpar_of(k - 1));  // peer is past k - 1 => it has mixed k - 3: row free
+                if (k >= 1) mbar_wait<kTx>(xbar_of(k - 1), xpar_of(k - 1));  // peer is past k - 1 => it has mixed k - 3: row free
                 asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(peer_wet + (uint32_t)(((int)(k % 3) * 2 + 1) * kRevMaxS) * 4u), "r"((uint32_t)__cvta_generic_to_shared(wown)),
                                "r"((uint32_t)(S * 4)), "r"(peer_xbar + 8u * (uint32_t)(k % 3)) : "memory");
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"((uint32_t)(8 * S * 4)) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"((uint32_t)(NSPLIT * S * 4)) : "memory");
             }
             __syncwarp();
             // relaxed: a release here would first drain these threads' just-issued global stores of the mix (~1 us, and the
@@ -1282,7 +1305,7 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
         for (int64_t m = max((int64_t)0, nsteps - 2); m < nsteps; ++m) {  // the last two super-steps are still unmixed
             float xd[kPerA];
             load_dry(m, xd);
-            mbar_wait_cluster(xbar_of(m), xpar_of(m));
+            mbar_wait<kTx>(xbar_of(m), xpar_of(m));
             mix(m, xd);
         }
         if (out_peak != nullptr) {

@@ -86,6 +86,7 @@ const Range kCompRanges[4] = {{-80, 0}, {1, 20}, {0.1, 100}, {10, 1000}};
 const Range kDistRanges[2] = {{-48, 48}, {-24, 24}};
 const Range kDelayRanges[3] = {{0.01, 1.0}, {0.05, 1.0}, {0.0, 1.0}};
 const Range kReverbRanges[4] = {{0, 1}, {0, 1}, {0, 1}, {0, 1}};
+const Range kLtiCompRanges[6] = {{-60, 0}, {1, 20}, {0.1, 250}, {10, 2000}, {1, 24}, {0, 24}};  // effects.py:629-634
 const Range kUnitRanges[STITO_MAX_FX_PARAMS] = {{0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1},
                                                 {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1},
                                                 {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}};
@@ -98,6 +99,7 @@ int fx_num_params(int kind) {
         case STITO_FX_DELAY: return 3;
         case STITO_FX_REVERB: return 4;
         case STITO_FX_CONV_REVERB: return 25;
+        case STITO_FX_LTI_COMPRESSOR: return 6;
     }
     return -1;
 }
@@ -109,6 +111,7 @@ const Range *fx_ranges(int kind) {
         case STITO_FX_DELAY: return kDelayRanges;
         case STITO_FX_REVERB: return kReverbRanges;
         case STITO_FX_CONV_REVERB: return kUnitRanges;
+        case STITO_FX_LTI_COMPRESSOR: return kLtiCompRanges;
     }
     return nullptr;
 }
@@ -271,6 +274,8 @@ int validate_chain(const stito_chain_desc *c) {
             if (d.iopt[0] < 2 || d.iopt[0] > 131072) return fail(STITO_EINVAL, "effect %d: impulse-response length %d outside [2, 131072]", f, d.iopt[0]);
             if (c->sample_rate < 36100.0) return fail(STITO_EINVAL, "effect %d: the 18 kHz band of the convolution reverb needs a sample rate above 36.1 kHz", f);
         }
+        if (d.kind == STITO_FX_LTI_COMPRESSOR && (d.iopt[0] < 0 || d.iopt[0] > (1 << 20)))
+            return fail(STITO_EINVAL, "effect %d: look-ahead of %d samples outside [0, 2^20]", f, d.iopt[0]);
         for (int k = 0; k < np; ++k)
             if (d.w_index[k] >= c->num_w) return fail(STITO_EINVAL, "effect %d parameter %d: w index %d >= D=%d", f, k, d.w_index[k], c->num_w);
     }
@@ -291,7 +296,7 @@ constexpr size_t kParamSlot = 6 * 5 * sizeof(double);  // largest: EQ coefficien
 
 // Host: de-normalise w and design every effect's constants for P candidates into hparams
 // ([fx][P][kParamSlot]); returns max delay length through *max_d.
-void design_params(const stito_chain_desc &c, const double *W, int P, int D, uint8_t *hp, int *max_d) {
+void design_params(const stito_chain_desc &c, const double *W, int P, int D, int64_t L, uint8_t *hp, int *max_d) {
     const double fs = c.sample_rate;
     *max_d = 1;
     for (int f = 0; f < c.num_fx; ++f) {
@@ -347,6 +352,11 @@ void design_params(const stito_chain_desc &c, const double *W, int P, int D, uin
                     ConvRevParams *q = reinterpret_cast<ConvRevParams *>(block) + p;
                     for (int b = 0; b < 12; ++b) { q->gain[b] = (float)v[b]; q->decay[b] = (float)v[12 + b]; }
                     q->mix = (float)v[24];
+                    break;
+                }
+                case STITO_FX_LTI_COMPRESSOR: {  // apply_compressor (effects.py:629-634); release_ms (v[3]) is unused upstream
+                    LtiCompParams *q = reinterpret_cast<LtiCompParams *>(block) + p;
+                    lticomp_design(fs, L, (float)v[0], (float)v[1], (float)v[2], (float)v[4], (float)v[5], q);
                     break;
                 }
                 case STITO_FX_REVERB: {  // BasicReverb.process (effects.py:952-959) + oracle_reverb
@@ -408,7 +418,7 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
     h->hparams_cursor += (pbytes + 255) & ~(size_t)255;
     CU(h->params.ensure(pbytes));
     int max_d = 1;
-    design_params(c, W_host, P, D, hslice, &max_d);
+    design_params(c, W_host, P, D, L, hslice, &max_d);
     CU(cudaMemcpyAsync(h->params.p, hslice, pbytes, cudaMemcpyHostToDevice, st));
 
     SigView cur = in;
@@ -472,6 +482,13 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
             case STITO_FX_CONV_REVERB: {
                 CU(convreverb_prepare(st, &h->crv, c.sample_rate, d.iopt[0], d.iopt[1]));
                 CU(launch_convreverb(st, &h->crv, cur, in_peak, out, P, L, reinterpret_cast<const ConvRevParams *>(slot), opk, launches));
+                break;
+            }
+            case STITO_FX_LTI_COMPRESSOR: {
+                const int link = (cur_chs == 2 && d.num_channels == 2) ? 2 : 1;
+                CU(h->eq_f.ensure(lticomp_scratch_bytes(P, cur_chs, link, L)));
+                CU(launch_lticomp(st, cur, in_peak, out, P, cur_chs, link, L, d.iopt[0], reinterpret_cast<const LtiCompParams *>(slot),
+                                  h->eq_f.p, opk, launches));
                 break;
             }
             case STITO_FX_REVERB: {
@@ -1145,6 +1162,17 @@ int stito_crv_host_filterbank(double sample_rate, float *out) {
 int stito_crv_host_noise(uint64_t seed, int64_t n, float *out) {
     if (!out || n < 0) return fail(STITO_EINVAL, "bad argument");
     convreverb_host_noise(seed, (size_t)n, out);
+    return STITO_OK;
+}
+
+/* Host-side design of STITO_FX_LTI_COMPRESSOR's smoothing filter, for the CPU tests: out = {alpha, 1 - alpha, wrap}. */
+int stito_lticomp_host_design(double sample_rate, int64_t L, float attack_ms, double *out) {
+    if (!out || !(sample_rate > 0) || L <= 0 || !(attack_ms > 0)) return fail(STITO_EINVAL, "bad argument");
+    LtiCompParams q;
+    lticomp_design(sample_rate, L, 0.0f, 1.0f, attack_ms, 1.0f, 0.0f, &q);
+    out[0] = q.alpha;
+    out[1] = q.b0;
+    out[2] = q.wrap;
     return STITO_OK;
 }
 

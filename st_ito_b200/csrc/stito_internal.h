@@ -91,6 +91,18 @@ void convreverb_release(ConvReverbState *s);
 void convreverb_host_filterbank(double sample_rate, float *out);
 void convreverb_host_noise(uint64_t seed, size_t count, float *out);
 
+// Compressor with LTI gain smoothing (lticomp.cu).  link = channels summed into one side-chain (1 or 2; chs % link == 0).
+struct LtiCompParams {
+    double alpha, b0, ln_alpha;  // one-pole smoothing y = alpha y + b0 g (alpha, b0 = float32 values of the reference)
+    double wrap;                 // y[-1] = y0[L-1] * wrap: periodic steady state of the frequency-sampled filter
+    float thr, ratio, knee, makeup;
+};
+void lticomp_design(double sample_rate, int64_t L, float threshold_db, float ratio, float attack_ms, float knee_db,
+                    float makeup_db, LtiCompParams *q);
+size_t lticomp_scratch_bytes(int P, int chs, int link, int64_t L);
+cudaError_t launch_lticomp(cudaStream_t st, SigView in, const float *in_peak, float *out, int P, int chs, int link, int64_t L,
+                           int lookahead, const LtiCompParams *prm, void *scratch, unsigned *out_peak, int *launches);
+
 // ------------------------------------------------------- front-end (frontend_kernels.cu)
 struct FrontendTables {
     float2 *twiddle;   // [n_fft] exp(-2*pi*i*k/n_fft)

@@ -168,6 +168,29 @@ class BasicNoiseShapedReverb2s(BasicNoiseShapedReverb):
         super().__init__(num_samples=96000, seed=0)
 
 
+class BasicLTICompressor(_BasicPlugin):
+    """Compressor with LTI gain smoothing, in the plugin protocol of the ES path.
+
+    The reference reaches this effect only through ``apply_compressor`` (effects.py:623-648, run_autodiff / the style
+    chain) and ``apply_random_compressor`` (dsp.py:49-78): dasp-pytorch's ``compressor``.  The six parameters and their
+    ranges are effects.py:629-634 (``release_ms`` is accepted and unused, as upstream); ``lookahead_samples`` = 512 is
+    effects.py:646.  ``num_channels: 2`` in the chain entry links the channels (summed side-chain, what the reference
+    does for a stereo tensor); ``1`` compresses every channel on its own.
+    """
+
+    stito_kind = _lib.FX_LTI_COMPRESSOR
+    _spec = (("threshold_db", -24.0, -60.0, 0.0), ("ratio", 4.0, 1.0, 20.0), ("attack_ms", 10.0, 0.1, 250.0),
+             ("release_ms", 100.0, 10.0, 2000.0), ("knee_db", 6.0, 1.0, 24.0), ("makeup_gain_db", 0.0, 0.0, 24.0))
+
+    def __init__(self, lookahead_samples: int = 512):
+        self.lookahead_samples = int(lookahead_samples)
+        self._init_parameters([s[1] for s in self._spec])
+
+    @property
+    def stito_iopt(self):
+        return (self.lookahead_samples, 0, 0, 0)
+
+
 def is_native_plugin(obj) -> bool:
     """True for plugins libstito can render (their ranges are the ones compiled into the library)."""
     if not isinstance(obj, _BasicPlugin) or obj.stito_kind < 0:
@@ -185,13 +208,15 @@ def make_chain(kind: str = "basic") -> dict:
     table = {
         "ParametricEQ": (BasicParametricEQ, 1), "Compressor": (BasicCompressor, 1),
         "Distortion": (BasicDistortion, 1), "Delay": (BasicDelay, 2), "Reverb": (BasicReverb, 2),
-        "NoiseShapedReverb": (BasicNoiseShapedReverb2s, 2),
+        "NoiseShapedReverb": (BasicNoiseShapedReverb2s, 2), "LTICompressor": (BasicLTICompressor, 2),
     }
     presets = {
         "basic": ["ParametricEQ", "Compressor", "Distortion", "Delay", "Reverb"],
         "mastering-pb": ["ParametricEQ", "Compressor", "Reverb"],
         "eq": ["ParametricEQ"],
         "mastering-conv": ["ParametricEQ", "Compressor", "NoiseShapedReverb"],  # BASELINE config 4
+        # SURVEY row R2 in full: the dasp-style pair of effects.py:558-648 behind the EQ
+        "mastering-dasp": ["ParametricEQ", "LTICompressor", "NoiseShapedReverb"],
     }
     if kind not in presets:
         raise ValueError(f"Unknown chain: {kind}")

@@ -66,7 +66,9 @@ def native_plugins(kinds, load=True):
              "dist": ("Distortion", effects.BasicDistortion, 1), "delay": ("Delay", effects.BasicDelay, 2),
              "reverb": ("Reverb", effects.BasicReverb, 2),
              "convreverb": ("NoiseShapedReverb", effects.BasicNoiseShapedReverb, 2),
-             "convreverb2s": ("NoiseShapedReverb", effects.BasicNoiseShapedReverb2s, 2)}
+             "convreverb2s": ("NoiseShapedReverb", effects.BasicNoiseShapedReverb2s, 2),
+             "lticomp": ("LTICompressor", effects.BasicLTICompressor, 2),
+             "lticomp1": ("LTICompressor", effects.BasicLTICompressor, 1)}
     plugins = {}
     for k in kinds:
         name, cls, ch = table[k]
@@ -995,6 +997,81 @@ def test_config4_as_stated_30s_conv_reverb(models_centred, oracle_dsp):
     err = np.abs(aud[0].numpy() - ref0)
     assert err.max() <= 3e-5 and err.mean() <= 5e-6, (err.max(), err.mean())
     np.testing.assert_array_equal(aud[2].numpy(), tgt)
+
+
+# ------------------------------------------------- compressor with LTI gain smoothing (second half)
+@pytest.mark.parametrize("chs", [1, 2])
+@pytest.mark.parametrize("L", [3000, 50001, 480000])
+def test_lti_compressor_matches_oracle(chs, L):
+    """apply_compressor's arithmetic (effects.py:623-648 -> dasp compressor) as an ES-path plugin: the chunk-parallel fp64
+    recursion (+ the wrap-around term of the reference's frequency-sampled filter, which matters at L = 3000 with a long
+    attack) against oracle/lticomp.py, whose smoothing is the float64 FFT method itself.  Parity unpinned upstream."""
+    from oracle.lticomp import OracleLTICompressor
+    from st_ito_b200 import effects
+
+    rng = np.random.RandomState(L + chs)
+    x = test_signal(chs, L, seed=70 + chs)
+    x = (0.7 * x / np.abs(x).max()).astype(np.float32)
+    corners = [np.array([0.0, 1.0, 1.0, 0.5, 0.0, 1.0]),   # threshold -60 dB, ratio 20, attack 250 ms, knee 1 dB, make-up 24 dB
+               np.array([0.5, 0.3, 0.0, 0.5, 1.0, 0.0]),   # attack 0.1 ms, knee 24 dB
+               np.array([1.0, 0.0, 0.5, 0.5, 0.5, 0.5])]   # threshold 0 dB, ratio 1: identity curve
+    for look in (512, 0):
+        ours, ref = effects.BasicLTICompressor(look), OracleLTICompressor(look)
+        for trial, raw in enumerate(corners + [rng.rand(6) for _ in range(3)]):
+            for p, q, v in zip(ours.parameters.values(), ref.parameters.values(), raw):
+                p.raw_value = float(v)
+                q.raw_value = float(v)
+            y = ours.process(x.copy(), SR)
+            want = ref.process(x.copy(), SR)
+            assert y.shape == want.shape == (chs, L) and y.dtype == np.float32
+            peak = np.abs(want).max()
+            assert np.abs(y - want).max() <= 1e-5 * peak, (look, trial, np.abs(y - want).max() / peak)
+            if look:
+                assert not y[:, :look].any()
+
+
+def test_lti_compressor_channel_policy_and_chain(models_centred, oracle_dsp):
+    """(1) num_channels = 1 on stereo audio: two independent mono passes (style_transfer.py:98-102), 2: linked side-chain;
+    (2) EQ -> LTI compressor -> noise-shaped reverb (make_chain("mastering-dasp"), D = 51) through evaluate()."""
+    from oracle import cnn14
+    from st_ito_b200.engine import compile_chain
+    from st_ito_b200.style_transfer import process_audio
+
+    L = 120001
+    x = test_signal(2, L, seed=17)
+    x = x / np.abs(x).max()
+    rng = np.random.RandomState(18)
+    for kind in ("lticomp1", "lticomp"):
+        plugins, D, _ = native_plugins([kind])
+        oplugins, oD, _ = oracle_plugins(oracle_dsp, [kind])
+        assert D == oD == 7
+        for w in rng.rand(3, D):
+            y = process_audio(x, w, SR, plugins)
+            want = oracle_dsp.process_audio(x, w, SR, oplugins)
+            assert np.abs(y - want).max() <= 1e-5, (kind, np.abs(y - want).max())
+    ours, ref = models_centred
+    eng = ours.stito_engine()
+    eng.set_precision(1)
+    kinds = ["eq", "lticomp", "convreverb"]
+    plugins, D, _ = native_plugins(kinds)
+    oplugins, oD, _ = oracle_plugins(oracle_dsp, kinds)
+    assert D == oD == 52
+    P = 5
+    w_star, W = rng.rand(D), rng.rand(P, D)
+    tgt = oracle_dsp.process_audio(x, w_star, SR, oplugins)
+    te = cnn14.get_param_embeds(torch.from_numpy(tgt[None].copy()), ref, SR)
+    want, oe, audios = oracle_population(oracle_dsp, x, W, oplugins, ref, te, pad=False)
+    desc, _ = compile_chain(plugins, SR)
+    eng.set_chain(desc)
+    eng.set_input(x)
+    eng.set_target_embeds(te["mid"][0], te["side"][0])
+    fit, emb, aud = eng.eval_population(W, 0, L, want_embeds=True, want_audio=True, in_chs=2)
+    assert_population_parity(fit.numpy(), want, emb, oe)
+    assert np.abs(aud.numpy() - audios.numpy()).max() <= 2e-5
+    # normalize_stages: the compressor divides its input by the previous stage's peak
+    y = process_audio(x, W[0], SR, plugins, normalize_stages=True)
+    wantn = oracle_dsp.process_audio(x, W[0], SR, oplugins, normalize_stages=True)
+    assert np.abs(y - wantn).max() <= 2e-5
 
 
 def test_many_microbatches_equal_separate_calls(models_centred):

@@ -1,0 +1,85 @@
+"""CPU tests of the compressor with LTI gain smoothing (second half): properties of the oracle
+restatement (oracle/lticomp.py -- parity unpinned upstream, dasp-pytorch is absent) and agreement of the host-side filter
+design libstito restates in C++ with the oracle's."""
+import numpy as np
+import pytest
+
+from tests.signals import test_signal
+
+SR = 48000
+
+
+@pytest.mark.parametrize("L,attack_ms", [(300, 250.0), (4096, 250.0), (5000, 100.0), (48000, 0.1), (48000, 250.0)])
+def test_frequency_sampling_equals_recursion_plus_wraparound(L, attack_ms):
+    """lfilter_via_fsm is a circular convolution: the recursion started from the periodic steady state, exactly."""
+    from scipy.signal import lfilter
+
+    from oracle import lticomp as lc
+
+    g = -10.0 * np.abs(np.random.RandomState(L).randn(L)).astype(np.float32)
+    a = lc.attack_alpha(attack_ms, SR)
+    fsm, rec = lc.smooth_gain_fsm(g, a), lc.smooth_gain_recursive(g, a)
+    np.testing.assert_allclose(rec, fsm, rtol=0, atol=1e-10)
+    y0 = lfilter([float(np.float32(1) - a)], [1.0, -float(a)], g.astype(np.float64))
+    wrap = np.abs(fsm - y0).max()
+    assert (wrap > 1.0) if (L <= 4096 and attack_ms == 250.0) else (wrap < 0.05)  # short clip + long attack: not negligible
+
+
+def test_libstito_filter_design_matches_the_oracle():
+    from oracle import lticomp as lc
+    from st_ito_b200 import _lib
+
+    lib = _lib.lib()
+    out = np.empty(3, dtype=np.float64)
+    for sr in (48000.0, 44100.0):
+        for L in (300, 4096, 50001, 480000):
+            for att in (0.1, 0.37, 1.0, 10.0, 99.9, 250.0):
+                assert lib.stito_lticomp_host_design(sr, L, att, out.ctypes.data) == 0
+                a = lc.attack_alpha(np.float32(att), sr)
+                assert out[0] == float(a) and out[1] == float(np.float32(1.0) - a)
+                n_fft = lc.fsm_fft_size(L)
+                want = np.exp(np.log(float(a)) * (n_fft - L)) / (-np.expm1(np.log(float(a)) * n_fft))
+                assert abs(out[2] - want) <= 1e-12 * max(want, 1e-300) + 1e-300
+    assert lib.stito_lticomp_host_design(48000.0, 0, 1.0, out.ctypes.data) < 0
+
+
+def test_oracle_compressor_properties():
+    from oracle import lticomp as lc
+
+    L = 30000
+    x = test_signal(2, L, seed=4)
+    x = (0.05 * x / np.abs(x).max()).astype(np.float32)
+    # far below the threshold: unit gain curve, only make-up gain and the look-ahead delay remain
+    y = lc.lti_compressor(x, SR, threshold_db=0.0, ratio=8.0, attack_ms=5.0, release_ms=100.0, knee_db=1.0,
+                          makeup_gain_db=6.0, lookahead_samples=512)
+    want = np.zeros_like(x)
+    want[:, 512:] = x[:, :-512] * np.float32(10.0 ** (6.0 / 20.0))
+    np.testing.assert_allclose(y, want, rtol=2e-6, atol=0)
+    # ratio 1: the curve is the identity whatever the level
+    y1 = lc.lti_compressor(20 * x, SR, -40.0, 1.0, 5.0, 100.0, 6.0, 0.0, 0)
+    np.testing.assert_allclose(y1, 20 * x, rtol=2e-6, atol=0)
+    # constant level far above the knee: the smoothed gain settles on the static curve T + (x_db - T) / R - x_db
+    c = np.full((1, L), 0.5, dtype=np.float32)
+    y2 = lc.lti_compressor(c, SR, -30.0, 4.0, 1.0, 100.0, 6.0, 0.0, 0)
+    x_db = 20 * np.log10(0.5)
+    g = -30.0 + (x_db + 30.0) / 4.0 - x_db
+    assert abs(20 * np.log10(y2[0, -1] / 0.5) - g) < 1e-3
+    # the side-chain is the SUM of the channels: a stereo pair of identical channels is driven 6 dB harder than mono
+    m = lc.lti_compressor(c, SR, -30.0, 4.0, 1.0, 100.0, 6.0, 0.0, 0)
+    s = lc.lti_compressor(np.concatenate([c, c]), SR, -30.0, 4.0, 1.0, 100.0, 6.0, 0.0, 0)
+    assert np.array_equal(s[0], s[1]) and abs(20 * np.log10(s[0, -1] / m[0, -1]) + 20 * np.log10(2.0) * 0.75) < 1e-3
+    # the release time is accepted and ignored (upstream behaviour)
+    assert np.array_equal(lc.lti_compressor(x, SR, -40.0, 4.0, 5.0, 10.0, 6.0, 0.0, 0),
+                          lc.lti_compressor(x, SR, -40.0, 4.0, 5.0, 2000.0, 6.0, 0.0, 0))
+
+
+def test_plugin_wrappers_agree_on_the_parameter_schema():
+    from oracle.lticomp import OracleLTICompressor
+    from st_ito_b200 import effects
+
+    a, b = effects.BasicLTICompressor(), OracleLTICompressor()
+    assert list(a.parameters) == list(b.parameters) and a.lookahead_samples == b.lookahead_samples == 512
+    for k in a.parameters:
+        assert (a.parameters[k].min_value, a.parameters[k].max_value) == (b.parameters[k].min_value, b.parameters[k].max_value)
+        assert a.parameters[k].raw_value == pytest.approx(b.parameters[k].raw_value)
+    assert effects.is_native_plugin(a) and list(effects.make_chain("mastering-dasp")) == ["ParametricEQ", "LTICompressor", "NoiseShapedReverb"]
