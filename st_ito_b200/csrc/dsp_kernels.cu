@@ -945,6 +945,7 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
 // Per super-step both sides are chain-bound at ~0.8 us instead of issue-bound at 2.2 us.
 constexpr int kRsDepth = 6;  // slots of the hand-off ring: one row per PRODUCER CTA and slot (the sum of its comb filters'
                              // delayed outputs), NSPLIT x 6 rows = what 8 x 3 single-comb rows used to take
+constexpr int kRsWet = 4;    // slots of the wet-row ring between the all-pass group of a home CTA and the two mixer groups
 template <int NSPLIT, int WPC> struct RsCfg {
     static constexpr int CW = 8 / NSPLIT;                  // comb filters per CTA
     static constexpr int kCombThreads = 32 * WPC * CW;     // WPC warps per comb filter
@@ -952,7 +953,7 @@ template <int NSPLIT, int WPC> struct RsCfg {
     static constexpr int kFloats = CW * kCombRing + NSPLIT * kRsDepth * kRevMaxS + 4 * kApRing + 2 * kRevMaxS + 6 * kRevMaxS +
                                    kRsDepth * kRevMaxS +       // staging of the delayed rows (source of the bulk copies)
                                    2 * CW * WPC * 2 + 2 * CW;  // per-warp scan totals (double-buffered float2) + carries
-    static constexpr size_t kSmem = (size_t)kFloats * sizeof(float) + (2 * kRsDepth + 4) * sizeof(uint64_t) + 16;
+    static constexpr size_t kSmem = (size_t)kFloats * sizeof(float) + (2 * kRsDepth + 2 * kRsWet) * sizeof(uint64_t) + 16;
 };
 
 // mbarrier waits of reverb_split_kernel, bounded (a protocol bug must trap, not hang the GPU).
@@ -999,11 +1000,11 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
     float *dly = ring + CW * kCombRing;                 // [NSPLIT][kRsDepth][kRevMaxS] delayed comb outputs, summed per producer CTA (home only)
     float *ap = dly + NSPLIT * kRsDepth * kRevMaxS;     // [4][kApRing]
     float *inbuf = ap + 4 * kApRing;                    // [2][kRevMaxS] reverb input (l + r) * 0.015 of super-steps k, k + 1
-    float *wetb = inbuf + 2 * kRevMaxS;                 // [3][2][kRevMaxS] wet rows of super-steps k, k - 1, k - 2: [k % 3][own, peer]
+    float *wetb = inbuf + 2 * kRevMaxS;                 // [kRsWet][kRevMaxS] wet rows staged for the mixers (home CTA; 6 rows reserved)
     float *stage = wetb + 6 * kRevMaxS;                 // [kRsDepth][kRevMaxS] delayed rows staged for the bulk copy
     float *wtot = stage + kRsDepth * kRevMaxS;          // [2][CW][WPC] float2: affine map of each warp's part of the damping scan
     float *carry = wtot + 2 * CW * WPC * 2;             // [2][CW] damping-filter state entering the next super-step
-    uint64_t *bars = reinterpret_cast<uint64_t *>(carry + 2 * CW);  // full[kRsDepth], free[kRsDepth], xbar[3]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(carry + 2 * CW);  // full[kRsDepth], free[kRsDepth], wfree[kRsWet], mixfull[kRsWet]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = blockIdx.x % (2 * NSPLIT);
     const int p = blockIdx.x / (2 * NSPLIT);
@@ -1024,14 +1025,16 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(1u));                // full: armed with NSPLIT rows of bytes
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (kRsDepth + s2)), "r"(1u));   // free: the home's all-pass group
         }
-        for (int s2 = 0; s2 < 3; ++s2)  // xbar: armed with one wet row of bytes
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + s2)), "r"(1u));
-        if (home) {  // arm the first phases: NSPLIT delayed rows of S floats per slot, one wet row of the peer channel per parity
+        for (int s2 = 0; s2 < kRsWet; ++s2) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + s2)), "r"(2u));           // wfree (home): both mixers
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + kRsWet + s2)), "r"(1u));  // mixfull (mixer): 2 wet rows of bytes
+        }
+        if (home)  // arm the first phases: NSPLIT delayed rows of S floats per slot
             for (int s2 = 0; s2 < kRsDepth; ++s2)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s2), "r"((uint32_t)(NSPLIT * S * 4)) : "memory");
-            for (int s2 = 0; s2 < 3; ++s2)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + s2)), "r"((uint32_t)(S * 4)) : "memory");
-        }
+        if (gq == 1)  // the mixer: one wet row from each channel's home per slot
+            for (int s2 = 0; s2 < kRsWet; ++s2)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + kRsWet + s2)), "r"((uint32_t)(2 * S * 4)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_barrier();  // every CTA of the cluster is resident, zeroed and initialised before anything is stored into it
@@ -1194,67 +1197,38 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
         }
     } else if (home) {
         // ------------------------------------------------------------------ all-pass group of the home CTA (consumer)
+        // Per super-step: wait for the NSPLIT delayed rows, run the 4 all-passes over 5 sub-blocks, hand the wet row to
+        // the two MIXER groups (below) by bulk copy, free the slot.  Nothing else: the dry/wet mix with its global loads
+        // and stores, and the L <-> R wet exchange, took 60 % of this group's time when it did them itself
+        // (profiles/r02e_reverb_split.md, v10) and this group is the slowest stage of the pipeline.
         const int a = tid - Cfg::kCombThreads;
         int ad[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) ad[j] = g.ap_delay[c][j];
-        float *dst = out + ((int64_t)p * 2 + c) * L;
-        const float *xc = c ? xr : xl;
-        float pk = 0.0f;
-        const uint32_t peer_wet = map_to((uint32_t)__cvta_generic_to_shared(wetb), peer_rank);
-        const uint32_t peer_xbar = map_to(bar0 + 8u * (2 * kRsDepth), peer_rank);
+        const uint32_t mix_own = map_to((uint32_t)__cvta_generic_to_shared(dly), home_rank + 1);        // wet[.][0] of my channel's mixer
+        const uint32_t mix_peer = map_to((uint32_t)__cvta_generic_to_shared(dly), peer_rank + 1);       // wet[.][1] of the other channel's
+        const uint32_t mixfull_own = map_to(bar0 + 8u * (2 * kRsDepth + kRsWet), home_rank + 1);
+        const uint32_t mixfull_peer = map_to(bar0 + 8u * (2 * kRsDepth + kRsWet), peer_rank + 1);
         uint32_t free_of[NSPLIT];
 #pragma unroll
         for (int gg = 0; gg < NSPLIT; ++gg) free_of[gg] = map_to(bar0 + 8u * kRsDepth, home_rank + gg);
         auto ap_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kRevSub) : "memory"); };
-        auto xbar_of = [&](int64_t m) { return bar0 + 8u * (2 * kRsDepth + (uint32_t)(m % 3)); };
-        auto xpar_of = [&](int64_t m) { return (uint32_t)((m / 3) & 1); };
-        // y = wet_own * wet1 + wet_peer * wet2 + x * dry for super-step m (the dry samples are re-read from global memory:
-        // L2 hits, and it frees the shared memory the third wet row needs)
-        constexpr int kPerA = (kRevMaxS + kRevSub - 1) / kRevSub;
-        auto load_dry = [&](int64_t m, float (&xd)[kPerA]) {  // issued a compute phase before mix(m) consumes them
-            const int64_t m0 = m * S;
-#pragma unroll
-            for (int t = 0; t < kPerA; ++t) {
-                const int i = a + t * kRevSub;
-                xd[t] = (i < S && m0 + i < L) ? __ldcg(xc + m0 + i) : 0.0f;
-            }
-        };
-        auto mix = [&](int64_t m, const float (&xd)[kPerA]) {
-            const float *wo = wetb + (int)(m % 3) * 2 * kRevMaxS, *wpeer = wo + kRevMaxS;
-            const int64_t m0 = m * S;
-            const int cnt = (int)min((int64_t)S, L - m0);
-#pragma unroll
-            for (int t = 0; t < kPerA; ++t) {
-                const int i = a + t * kRevSub;
-                if (i < cnt) {
-                    const float y = __fadd_rn(__fadd_rn(__fmul_rn(wo[i], q.wet1), __fmul_rn(wpeer[i], q.wet2)), __fmul_rn(xd[t], q.dry));
-                    dst[m0 + i] = y;
-                    pk = fmaxf(pk, fabsf(y));
-                }
-            }
-        };
-        // The wet exchange with the other channel is kept OFF the critical loop: super-step m is mixed two super-steps
-        // later (its peer row has long landed), and the only wait for the peer -- "your super-step k - 1 row has arrived",
-        // which also proves that the peer has mixed k - 3 and so freed the row this step's copy will overwrite -- sits at
-        // the END of super-step k, one compute phase after the peer sent it.  (Waiting for row k - 1 at the START of
-        // super-step k put a DSMEM round trip into every iteration: 2.3 us per super-step instead of < 1.)
+        int slot = 0, ws = 0;
+        uint32_t full_par = 0, wfree_par = 1;  // wfree: first wait (k = kRsWet) is for phase 0, so the parity starts at 1 ^ 1
+        int nbase = 0;
         for (int64_t k = 0; k < nsteps; ++k) {
-            const int64_t n0 = k * S;
-            const int nbase = (int)(n0 & (kApRing * 1024 - 1));
-            const int slot = (int)(k % kRsDepth);
-            // (streaming pair: the dry samples of super-step k - 2 read below were published before the comb groups could
-            // compute the rows of super-step k - 2, which this group has consumed through full[] -- no flag to poll here)
-            float xd[kPerA];
-            if (k >= 2) load_dry(k - 2, xd);  // dry samples of the super-step mixed at the end of this one: in flight during the all-passes
-            mbar_wait<kTx>(bar0 + 8u * slot, (uint32_t)((k / kRsDepth) & 1));  // the NSPLIT delayed rows of this super-step
+            // the staging row of the wet samples is free once BOTH mixers have consumed super-step k - kRsWet (which also
+            // means the two bulk copies out of it are complete); control only, and long since true in steady state
+            if (k >= kRsWet && ws == 0) wfree_par ^= 1u;
+            if (k >= kRsWet) mbar_wait<kControl>(bar0 + 8u * (2 * kRsDepth + ws), wfree_par);
+            mbar_wait<kTx>(bar0 + 8u * slot, full_par);  // the NSPLIT delayed rows of this super-step
             const float *row = dly + slot * kRevMaxS;
-            float *wown = wetb + (int)(k % 3) * 2 * kRevMaxS;
+            float *wown = wetb + ws * kRevMaxS;
             for (int sb = 0; sb < nsub; ++sb) {
                 const int off = sb * kRevSub + a;
                 if (off < S) {
                     const int n = nbase + off;
-                    // all 12 shared-memory loads up front: the four all-pass rings are distinct arrays and each stage reads
+                    // all 8 shared-memory loads up front: the four all-pass rings are distinct arrays and each stage reads
                     // >= 244 samples behind what this sub-block writes, but the compiler cannot know and would serialise every
                     // stage's load behind the previous stage's store (4 x ~30 cycles of latency on the critical chain)
                     float cr[NSPLIT], bvv[4];
@@ -1273,40 +1247,82 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
                     }
                     wown[off] = v;
                 }
-                if (sb == nsub - 1) {
-                    if (k >= 2) {  // mix super-step k - 2: its peer row landed a whole super-step ago (acquire only)
-                        mbar_wait<kTx>(xbar_of(k - 2), xpar_of(k - 2));
-                        if (a == 0)  // re-arm this barrier for the peer's super-step k + 1
-                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xbar_of(k - 2)), "r"((uint32_t)(S * 4)) : "memory");
-                        mix(k - 2, xd);
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // wet samples -> visible to the bulk copy
-                }
-                ap_bar();  // after the last sub-block: everybody has also finished reading the rows mix(k - 2) used
+                if (sb == nsub - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // wet samples -> visible to the bulk copies
+                ap_bar();
             }
             // Every all-pass thread has passed the barrier above: the wet row of this super-step is complete and dly[.][slot]
-            // has been read.  ONE thread ships the wet row to the peer channel's home CTA (bulk copy through distributed shared
-            // memory, completing on the peer's xbar) and re-arms the slot; NSPLIT threads tell one producer CTA each that the
+            // has been read.  ONE thread hands the wet row to the mixer of this channel (as its "own" row) and to the mixer of
+            // the other channel (as its "peer" row) and re-arms the slot; NSPLIT threads tell one producer CTA each that the
             // slot (and its staging row) is free.
             if (a == 0) {
-                if (k >= 1) mbar_wait<kTx>(xbar_of(k - 1), xpar_of(k - 1));  // peer is past k - 1 => it has mixed k - 3: row free
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(wown);
                 asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(peer_wet + (uint32_t)(((int)(k % 3) * 2 + 1) * kRevMaxS) * 4u), "r"((uint32_t)__cvta_generic_to_shared(wown)),
-                               "r"((uint32_t)(S * 4)), "r"(peer_xbar + 8u * (uint32_t)(k % 3)) : "memory");
+                             ::"r"(mix_own + (uint32_t)((ws * 2 + 0) * kRevMaxS) * 4u), "r"(src), "r"((uint32_t)(S * 4)), "r"(mixfull_own + 8u * ws) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(mix_peer + (uint32_t)((ws * 2 + 1) * kRevMaxS) * 4u), "r"(src), "r"((uint32_t)(S * 4)), "r"(mixfull_peer + 8u * ws) : "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"((uint32_t)(NSPLIT * S * 4)) : "memory");
             }
             __syncwarp();
-            // relaxed: a release here would first drain these threads' just-issued global stores of the mix (~1 us, and the
-            // whole group then waits for them at the next barrier); what has to be ordered -- every thread's READS of
-            // dly[.][slot] -- completed before the barrier above
+            // relaxed: what has to be ordered -- every thread's READS of dly[.][slot] -- completed before the barrier above
             if (a < NSPLIT)
                 asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_of[a] + 8u * slot) : "memory");
+            if (++slot == kRsDepth) { slot = 0; full_par ^= 1u; }
+            if (++ws == kRsWet) ws = 0;
+            nbase = (nbase + S) & (kApRing * 1024 - 1);
         }
-        for (int64_t m = max((int64_t)0, nsteps - 2); m < nsteps; ++m) {  // the last two super-steps are still unmixed
-            float xd[kPerA];
-            load_dry(m, xd);
-            mbar_wait<kTx>(xbar_of(m), xpar_of(m));
-            mix(m, xd);
+    } else if (gq == 1) {
+        // ------------------------------------------------------------------ mixer group (CTA g == 1 of each channel)
+        // y = wet_own * wet1 + wet_peer * wet2 + x * dry.  The two wet rows of a super-step arrive by bulk copy from the two
+        // home CTAs (complete_tx on mixfull[ws]); the dry samples are re-read from global memory (L2 hits), prefetched one
+        // super-step ahead -- in the streaming pair that is safe: when mixfull of super-step m completes, every producer
+        // had acquired the input up to (m + 3) S before it staged its row m.  This CTA is not a home, so its dly region is
+        // free: wet[kRsWet][2][kRevMaxS] lives there.
+        const int a = tid - Cfg::kCombThreads;
+        const float *wet = dly;
+        float *dst = out + ((int64_t)p * 2 + c) * L;
+        const float *xc = c ? xr : xl;
+        float pk = 0.0f;
+        const uint32_t mixfull0 = bar0 + 8u * (2 * kRsDepth + kRsWet);
+        const uint32_t wfree_own = map_to(bar0 + 8u * (2 * kRsDepth), home_rank);
+        const uint32_t wfree_peer = map_to(bar0 + 8u * (2 * kRsDepth), peer_rank);
+        auto mx_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kRevSub) : "memory"); };
+        constexpr int kPerA = (kRevMaxS + kRevSub - 1) / kRevSub;
+        auto load_dry = [&](int64_t m, float (&xd)[kPerA]) {
+            const int64_t m0 = m * S;
+#pragma unroll
+            for (int t = 0; t < kPerA; ++t) {
+                const int i = a + t * kRevSub;
+                xd[t] = (i < S && m0 + i < L) ? __ldcg(xc + m0 + i) : 0.0f;
+            }
+        };
+        float xd[kPerA], xn[kPerA];
+        int ws = 0;
+        uint32_t par = 0;
+        for (int64_t m = 0; m < nsteps; ++m) {
+            mbar_wait<kTx>(mixfull0 + 8u * ws, par);
+            if (m == 0) load_dry(0, xd);
+            load_dry(m + 1, xn);
+            const float *wo = wet + ws * 2 * kRevMaxS, *wpeer = wo + kRevMaxS;
+            const int64_t m0 = m * S;
+            const int cnt = (int)min((int64_t)S, L - m0);
+#pragma unroll
+            for (int t = 0; t < kPerA; ++t) {
+                const int i = a + t * kRevSub;
+                if (i < cnt) {
+                    const float y = __fadd_rn(__fadd_rn(__fmul_rn(wo[i], q.wet1), __fmul_rn(wpeer[i], q.wet2)), __fmul_rn(xd[t], q.dry));
+                    dst[m0 + i] = y;
+                    pk = fmaxf(pk, fabsf(y));
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < kPerA; ++t) xd[t] = xn[t];
+            mx_bar();  // every mixer thread has read wet[ws]
+            if (a == 0) {  // re-arm the slot, then return the credit to both homes (relaxed: control only, see above)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mixfull0 + 8u * ws), "r"((uint32_t)(2 * S * 4)) : "memory");
+                asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(wfree_own + 8u * ws) : "memory");
+                asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(wfree_peer + 8u * ws) : "memory");
+            }
+            if (++ws == kRsWet) { ws = 0; par ^= 1u; }
         }
         if (out_peak != nullptr) {
             pk = warp_max(pk);
