@@ -930,29 +930,33 @@ __global__ void __launch_bounds__(kRevThreads, 1) reverb_core_kernel(SigView in,
 }
 
 // ------------------------------------------- reverb, split over a cluster (small populations)
-// With P * chs <= ~40 streams the kernel above leaves three quarters of the GPU idle while every CTA is issue-bound on
-// its 8 comb warps (2.2 us per super-step, 429 super-steps for 10 s).  Here one stereo candidate is a cluster of
-// 2 * NSPLIT CTAs: channel c = rank / NSPLIT, comb group g = rank % NSPLIT.
-//   * every CTA runs CW = 8 / NSPLIT comb filters (one warp each, same arithmetic as above) as a free-running producer;
-//     after super-step k it hands the home CTA of its channel (g == 0) the delayed comb outputs that the all-pass chain
-//     of super-step k + 1 will sum -- ONE row per producer CTA, dly[g][slot][i] = sum over its combs of ring_j[n - delay_j] --
-//     by a bulk copy through distributed shared memory that completes on the home CTA's full[slot] mbarrier;
-//   * the home CTA's all-pass group (224 threads) waits (acquire) on full[slot], adds the NSPLIT rows (pairwise order
-//     (c0 + c1) + (c2 + c3) + ...: within 1 ulp of reverb_core_kernel's left-to-right sum), runs the 4 all-passes,
-//     exchanges wet samples with the other channel's home CTA
-//     (same protocol as above) and mixes; when it is done with a slot it arrives on the free[slot] mbarrier of the NSPLIT
-//     producers.  A ring of kRsDepth slots decouples the two sides: there is no CTA-wide barrier in the loop.
-// Per super-step both sides are chain-bound at ~0.8 us instead of issue-bound at 2.2 us.
-constexpr int kRsDepth = 6;  // slots of the hand-off ring: one row per PRODUCER CTA and slot (the sum of its comb filters'
-                             // delayed outputs), NSPLIT x 6 rows = what 8 x 3 single-comb rows used to take
-constexpr int kRsWet = 4;    // slots of the wet-row ring between the all-pass group of a home CTA and the two mixer groups
-template <int NSPLIT, int WPC> struct RsCfg {
-    static constexpr int CW = 8 / NSPLIT;                  // comb filters per CTA
-    static constexpr int kCombThreads = 32 * WPC * CW;     // WPC warps per comb filter
+// With P * chs <= ~40 streams the kernel above leaves three quarters of the GPU idle while every CTA is bound by the
+// dependent chains of its 8 comb warps (2.2 us per super-step, 429 super-steps for 10 s).  Here one stereo candidate is a
+// cluster of 8 CTAs, 4 per channel (c = rank / 4, g = rank % 4), and every stage of the Freeverb gets its own SM(s):
+//   g == 0  "home": the ALL-PASS group only (224 threads).  Per super-step it waits (transaction barrier full[slot]) for the
+//           three producer rows, adds them, runs the 4 all-passes over 5 sub-blocks, hands the wet row to the two mixer
+//           groups by bulk copy and frees the slot.  It is the serial stage of the pipeline, so it shares its SM with nobody:
+//           with two comb filters next to it the SM's issue slots were the bottleneck (1.55 us per super-step, v11 below).
+//   g == 1..3  PRODUCERS: 2, 3 and 3 comb filters (WPC warps each, SEGL samples per lane, cross-warp affine scan of the
+//           damping filter).  After super-step k a producer stages ONE row -- the sum of its combs' delayed outputs that the
+//           all-pass chain of super-step k + 1 needs, dly[g][slot][i] = sum_j ring_j[n - delay_j] -- and one lane hands it to
+//           the bulk-copy engine (cp.async.bulk shared::cta -> shared::cluster, complete_tx on the home's full[slot]).  A ring
+//           of kRsDepth slots decouples producers and consumer; free[slot] (home -> producers) returns the credit.
+//   g == 1  also hosts the MIXER group of the channel (224 threads): y = wet_own * wet1 + wet_peer * wet2 + x * dry from the
+//           wet rows of BOTH channels' homes (bulk copies completing on mixfull[ws], ring of kRsWet rows, credit wfree) and the
+//           dry samples re-read from global memory one super-step ahead.
+// The sum of the 8 comb outputs is formed as ((c0 + c1) + ((c2 + c3) + c4)) + ((c5 + c6) + c7): within an ulp of
+// reverb_core_kernel's left-to-right sum.  Development log with ncu source-level measurements: profiles/r02e_reverb_split.md.
+constexpr int kRsDepth = 6;  // slots of the producer -> all-pass ring (one row per producer CTA and slot)
+constexpr int kRsWet = 4;    // slots of the all-pass -> mixer ring (wet rows)
+constexpr int kRsProd = 3;   // producer CTAs per channel
+constexpr int kRsMaxCw = 3;  // comb filters per producer CTA: 2, 3, 3
+template <int WPC> struct RsCfg {
+    static constexpr int kCombThreads = 32 * WPC * kRsMaxCw;
     static constexpr int kThreads = kCombThreads + kRevSub;
-    static constexpr int kFloats = CW * kCombRing + NSPLIT * kRsDepth * kRevMaxS + 4 * kApRing + 2 * kRevMaxS + 6 * kRevMaxS +
-                                   kRsDepth * kRevMaxS +       // staging of the delayed rows (source of the bulk copies)
-                                   2 * CW * WPC * 2 + 2 * CW;  // per-warp scan totals (double-buffered float2) + carries
+    static constexpr int kFloats = kRsMaxCw * kCombRing + kRsProd * kRsDepth * kRevMaxS + 4 * kApRing + 2 * kRevMaxS +
+                                   kRsWet * kRevMaxS + kRsDepth * kRevMaxS +      // wet rows / delayed rows staged for the bulk copies
+                                   2 * kRsMaxCw * WPC * 2 + 2 * kRsMaxCw + 2;     // per-warp scan totals (float2, double-buffered) + carries
     static constexpr size_t kSmem = (size_t)kFloats * sizeof(float) + (2 * kRsDepth + 2 * kRsWet) * sizeof(uint64_t) + 16;
 };
 
@@ -988,29 +992,32 @@ template <MbarWait MODE> __device__ __forceinline__ void mbar_wait(uint32_t bar,
 }
 
 // SEGL samples per lane, WPC warps per comb filter: S = 32 * WPC * SEGL samples per super-step (7 x 5 -> 1120, 8 x 4 -> 1024)
-template <int SEGL, int WPC, int NSPLIT>
-__global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_kernel(SigView in, float *out, int64_t L,
-                                                                                      ReverbFastGeom g, const ReverbParams *prm,
-                                                                                      unsigned *out_peak, const int *ready) {
-    using Cfg = RsCfg<NSPLIT, WPC>;
-    constexpr int CW = Cfg::CW, S = 32 * WPC * SEGL, RL = 3 * S;
+template <int SEGL, int WPC>
+__global__ void __launch_bounds__(RsCfg<WPC>::kThreads, 1) reverb_split_kernel(SigView in, float *out, int64_t L, ReverbFastGeom g,
+                                                                              const ReverbParams *prm, unsigned *out_peak,
+                                                                              const int *ready) {
+    using Cfg = RsCfg<WPC>;
+    constexpr int S = 32 * WPC * SEGL, RL = 3 * S;
     constexpr int nsub = (S + kRevSub - 1) / kRevSub;
     extern __shared__ float sm[];
-    float *ring = sm;                                   // [CW][kCombRing] my comb filters
-    float *dly = ring + CW * kCombRing;                 // [NSPLIT][kRsDepth][kRevMaxS] delayed comb outputs, summed per producer CTA (home only)
-    float *ap = dly + NSPLIT * kRsDepth * kRevMaxS;     // [4][kApRing]
-    float *inbuf = ap + 4 * kApRing;                    // [2][kRevMaxS] reverb input (l + r) * 0.015 of super-steps k, k + 1
-    float *wetb = inbuf + 2 * kRevMaxS;                 // [kRsWet][kRevMaxS] wet rows staged for the mixers (home CTA; 6 rows reserved)
-    float *stage = wetb + 6 * kRevMaxS;                 // [kRsDepth][kRevMaxS] delayed rows staged for the bulk copy
-    float *wtot = stage + kRsDepth * kRevMaxS;          // [2][CW][WPC] float2: affine map of each warp's part of the damping scan
-    float *carry = wtot + 2 * CW * WPC * 2;             // [2][CW] damping-filter state entering the next super-step
-    uint64_t *bars = reinterpret_cast<uint64_t *>(carry + 2 * CW);  // full[kRsDepth], free[kRsDepth], wfree[kRsWet], mixfull[kRsWet]
+    float *ring = sm;                                     // [kRsMaxCw][kCombRing] my comb filters (producers)
+    float *dly = ring + kRsMaxCw * kCombRing;             // home: [kRsProd][kRsDepth][kRevMaxS] delayed rows; g == 1: the mixer's wet[kRsWet][2][kRevMaxS]
+    float *ap = dly + kRsProd * kRsDepth * kRevMaxS;      // [4][kApRing] (home)
+    float *inbuf = ap + 4 * kApRing;                      // [2][kRevMaxS] reverb input (l + r) * 0.015 of super-steps k, k + 1 (producers)
+    float *wetb = inbuf + 2 * kRevMaxS;                   // [kRsWet][kRevMaxS] wet rows staged for the mixers (home)
+    float *stage = wetb + kRsWet * kRevMaxS;              // [kRsDepth][kRevMaxS] delayed rows staged for the bulk copy (producers)
+    float *wtot = stage + kRsDepth * kRevMaxS;            // [2][kRsMaxCw][WPC] float2: affine map of each warp's part of the damping scan
+    float *carry = wtot + 2 * kRsMaxCw * WPC * 2;         // [2][kRsMaxCw] damping-filter state entering the next super-step
+    uint64_t *bars = reinterpret_cast<uint64_t *>(carry + 2 * kRsMaxCw + 2);  // full[kRsDepth], free[kRsDepth], wfree[kRsWet], mixfull[kRsWet]
+    static_assert((Cfg::kFloats % 2) == 0 && ((kRsMaxCw * kCombRing) % 4) == 0 && (kRevMaxS % 4) == 0 && (kApRing % 4) == 0, "alignment");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rank = blockIdx.x % (2 * NSPLIT);
-    const int p = blockIdx.x / (2 * NSPLIT);
-    const int c = rank / NSPLIT, gq = rank % NSPLIT;
+    const int rank = blockIdx.x % 8;
+    const int p = blockIdx.x / 8;
+    const int c = rank / 4, gq = rank % 4;
     const bool home = gq == 0;
-    const uint32_t home_rank = (uint32_t)(c * NSPLIT), peer_rank = (uint32_t)((c ^ 1) * NSPLIT);
+    const int ncomb = home ? 0 : (gq == 1 ? 2 : 3);                 // comb filters of this CTA ...
+    const int comb0 = gq == 1 ? 0 : (gq == 2 ? 2 : 5);              // ... starting at this global index
+    const uint32_t home_rank = (uint32_t)(c * 4), peer_rank = (uint32_t)((c ^ 1) * 4);
     for (int i = tid; i < Cfg::kFloats; i += Cfg::kThreads) sm[i] = 0.0f;
     const ReverbParams q = prm[p];
     const int64_t nsteps = (L + S - 1) / S;
@@ -1022,16 +1029,16 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
     };
     if (tid == 0) {
         for (int s2 = 0; s2 < kRsDepth; ++s2) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(1u));                // full: armed with NSPLIT rows of bytes
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (kRsDepth + s2)), "r"(1u));   // free: the home's all-pass group
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s2), "r"(1u));                // full (home): kRsProd rows of bytes
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (kRsDepth + s2)), "r"(1u));   // free (producers): the home's all-pass group
         }
         for (int s2 = 0; s2 < kRsWet; ++s2) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + s2)), "r"(2u));           // wfree (home): both mixers
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + kRsWet + s2)), "r"(1u));  // mixfull (mixer): 2 wet rows of bytes
         }
-        if (home)  // arm the first phases: NSPLIT delayed rows of S floats per slot
+        if (home)  // arm the first phases: one delayed row of S floats per producer and slot
             for (int s2 = 0; s2 < kRsDepth; ++s2)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s2), "r"((uint32_t)(NSPLIT * S * 4)) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s2), "r"((uint32_t)(kRsProd * S * 4)) : "memory");
         if (gq == 1)  // the mixer: one wet row from each channel's home per slot
             for (int s2 = 0; s2 < kRsWet; ++s2)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * (2 * kRsDepth + kRsWet + s2)), "r"((uint32_t)(2 * S * 4)) : "memory");
@@ -1053,14 +1060,27 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
     const float *xl = in.base + (int64_t)p * in.stride_p;
     const float *xr = xl + in.stride_c;
 
-    if (tid < Cfg::kCombThreads) {
-        // ------------------------------------------------------------------ comb group (producer)
+    // Roles of this CTA's threads.  Producer CTAs: comb warps (cw < ncomb) and a STAGER group that builds and ships the
+    // rows for the all-pass chain concurrently with the comb warps' next super-step -- g == 1: the unused third comb slot
+    // (32 * WPC threads; the 224 threads behind the comb slots are the mixer); g == 2, 3: the 224 threads behind the comb slots.
+    const bool comb_slot = tid < Cfg::kCombThreads;
+    const int cw = warp / WPC, ww = warp % WPC;
+    const bool is_comb = comb_slot && cw < ncomb;
+    const bool is_stager = !home && (gq == 1 ? (comb_slot && cw == 2) : !comb_slot);
+    const int nthr = 32 * WPC * ncomb;                     // comb threads of this CTA (320 or 480 at WPC = 5)
+    const int nst = gq == 1 ? 32 * WPC : kRevSub;          // stager threads
+    auto comb_bar = [&]() { asm volatile("bar.sync 2, %0;" ::"r"(nthr) : "memory"); };                  // (A): comb warps
+    auto ring_bar = [&]() { asm volatile("bar.sync 3, %0;" ::"r"(nthr + nst) : "memory"); };            // (B): comb warps + stagers
+    auto stager_bar = [&]() { asm volatile("bar.sync 4, %0;" ::"r"(nst) : "memory"); };
+
+    if (is_comb) {
+        // ------------------------------------------------------------------ comb group (producer CTAs)
         // One comb filter = WPC warps; lane l = ww * 32 + lane of the comb owns SEGL consecutive samples of the super-step.
         // (One warp per comb with 35 samples per lane is a ~980-instruction dependent chain per super-step -- 2 us, which
-        // is what bounds reverb_core_kernel as well; ncu source view in profiles/r02e_reverb_split.md.)
-        const int cw = warp / WPC, ww = warp % WPC;
-        const int jg = gq * CW + cw;                   // global comb index 0..7 of channel c
-        const int my_delay = g.comb_delay[c][jg];
+        // is what bounds reverb_core_kernel as well.)  The loop is bound by its own dependent chains (clock trace in
+        // profiles/r02e_reverb_split.md: ~930 cycles to barrier (A), ~720 to barrier (B)), so everything that is not the
+        // recurrence -- building and shipping rows, flag polling, credit waits -- lives in the stager group.
+        const int my_delay = g.comb_delay[c][comb0 + cw];
         float *my_ring = ring + cw * kCombRing;
         const float keep = __fsub_rn(1.0f, q.damp);
         float dpow = 1.0f;
@@ -1068,15 +1088,13 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
         for (int i = 0; i < SEGL; ++i) dpow = __fmul_rn(dpow, q.damp);
         const int lc = ww * 32 + lane;                 // lane index inside the comb
         const int i0 = lc * SEGL;
-        const uint32_t dly_home = map_to((uint32_t)__cvta_generic_to_shared(dly), home_rank);
-        const uint32_t full_home = map_to(bar0, home_rank);
-        // stage the reverb input of one super-step: thread t handles flat indices t, t + T, ... of [S] (l, r summed)
-        constexpr int kPerT = (kRevMaxS + Cfg::kCombThreads - 1) / Cfg::kCombThreads;
+        // stage the reverb input of one super-step: thread t handles flat indices t, t + nthr, ... of [S] (l, r summed)
+        constexpr int kPerT = (kRevMaxS + 32 * WPC * 2 - 1) / (32 * WPC * 2);  // sized for the smallest group (2 combs)
         float pl[kPerT], pr[kPerT];
         auto fetch_in = [&](int64_t base) {
 #pragma unroll
             for (int k = 0; k < kPerT; ++k) {
-                const int i = tid + k * Cfg::kCombThreads;
+                const int i = tid + k * nthr;
                 const int64_t n = base + i;
                 const bool ok = i < S && n < L;
                 pl[k] = ok ? __ldcg(xl + n) : 0.0f;
@@ -1087,68 +1105,22 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
             float *dst = inbuf + b * kRevMaxS;
 #pragma unroll
             for (int k = 0; k < kPerT; ++k) {
-                const int i = tid + k * Cfg::kCombThreads;
+                const int i = tid + k * nthr;
                 if (i < S) dst[i] = __fmul_rn(__fadd_rn(pl[k], pr[k]), 0.015f);
             }
         };
-        auto comb_bar = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(Cfg::kCombThreads) : "memory"); };
-        // Delayed outputs for the all-pass chain of super-step m: the S samples are one contiguous run of my ring (it
-        // continues into the mirror, never wraps).  The comb's warps copy it into a 16-byte aligned staging row
-        // (stage_row); after the next CTA barrier ONE lane hands the row to the bulk-copy engine (ship_row), which writes the
-        // home CTA's dly row through distributed shared memory and completes the transaction on the home's full[slot]
-        // mbarrier -- no remote stores and no release fence on the comb filters' critical path.  The staging row is reused
-        // for super-step m + depth, i.e. only after free[slot] said that the all-pass group has consumed this one.
-        auto stage_row = [&](int64_t m) {
-            const int slot = (int)(m % kRsDepth);  // free: wait_free(m) by one thread + a comb barrier precede this call
-            // the row this CTA contributes = sum of its CW comb filters' delayed runs (fixed order: comb 0 + comb 1 + ...);
-            // every comb thread of the CTA handles at most one 16-byte group
-            const int wb = (int)(m % 3) * S;
-            float *srow = stage + slot * kRevMaxS;
-            for (int v4 = tid; v4 < S / 4; v4 += Cfg::kCombThreads) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int cq = 0; cq < CW; ++cq) {
-                    int rb = wb - g.comb_delay[c][gq * CW + cq];
-                    if (rb < 0) rb += RL;
-                    const float *src = ring + cq * kCombRing + rb + 4 * v4;
-                    if (cq == 0) acc = make_float4(src[0], src[1], src[2], src[3]);
-                    else { acc.x = __fadd_rn(acc.x, src[0]); acc.y = __fadd_rn(acc.y, src[1]); acc.z = __fadd_rn(acc.z, src[2]); acc.w = __fadd_rn(acc.w, src[3]); }
-                }
-                *reinterpret_cast<float4 *>(srow + 4 * v4) = acc;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my staging writes -> visible to the async proxy
-        };
-        auto wait_free = [&](int64_t m) {  // one thread: the home's all-pass group has finished super-step m - depth, which
-            if (m >= kRsDepth) {           // read this slot (so the bulk copy out of its staging row is long complete)
-                const int slot = (int)(m % kRsDepth);
-                mbar_wait<kControl>(bar0 + 8u * (kRsDepth + slot), (uint32_t)(((m / kRsDepth) - 1) & 1));
-            }
-        };
-        auto ship_row = [&](int64_t m) {  // after a CTA barrier that follows stage_row(m): ONE bulk copy per producer CTA
-            if (tid == 0) {
-                const int slot = (int)(m % kRsDepth);
-                const float *srow = stage + slot * kRevMaxS;
-                const uint32_t dst = dly_home + (uint32_t)((gq * kRsDepth + slot) * kRevMaxS) * 4u;
-                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(dst), "r"((uint32_t)__cvta_generic_to_shared(srow)), "r"((uint32_t)(S * 4)), "r"(full_home + 8u * slot)
-                             : "memory");
-            }
-        };
-        if (ready != nullptr && tid == 0) need_input(3 * (int64_t)S);
-        if (ready != nullptr) comb_bar();
+        ring_bar();    // (B) of the prologue: the stager's thread 0 has acquired the input up to 3 S (streaming pair)
         fetch_in(0);
         park_in(0);
         fetch_in(S);   // registers: the input of super-step 1, parked at the start of super-step 0
-        stage_row(0);  // all zeros: nothing has been written to the rings yet
-        if (lc == 0) { carry[cw] = 0.0f; carry[CW + cw] = 0.0f; }
+        if (lc == 0) { carry[cw] = 0.0f; carry[kRsMaxCw + cw] = 0.0f; }
         comb_bar();
-        ship_row(0);
         int wbase = 0;
         for (int64_t k = 0; k < nsteps; ++k, wbase = (wbase == 2 * S) ? 0 : wbase + S) {
             const int par = (int)(k & 1);
             // input pipeline: the registers hold super-step k + 1 (loaded a whole super-step ago: an L2 round trip no longer
             // shows up as a stall); park it -- inbuf[par ^ 1] was last read before barrier (B) of super-step k - 1 -- and
-            // start the loads of super-step k + 2
+            // start the loads of super-step k + 2 (the stager acquired them before that barrier)
             park_in(par ^ 1);
             fetch_in((k + 2) * S);
             const float *inb = inbuf + par * kRevMaxS;
@@ -1169,11 +1141,10 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
                 const float Bp = __shfl_up_sync(0xffffffffu, Bv, d);
                 if (lane >= d) { Bv = fmaf(Bp, A, Bv); A = A * Ap; }
             }
-            float2 *wt = reinterpret_cast<float2 *>(wtot) + (par * CW + cw) * WPC;
+            float2 *wt = reinterpret_cast<float2 *>(wtot) + (par * kRsMaxCw + cw) * WPC;
             if (lane == 31) wt[ww] = make_float2(A, Bv);
-            comb_bar();                 // (A) warp totals + last step's carry visible; row k staged by everybody
-            if (k > 0) ship_row(k);     // one lane hands the row staged at the end of the previous super-step to the copy engine
-            float s_in = carry[par * CW + cw];  // state entering this super-step, then through the warps before mine
+            comb_bar();                 // (A) warp totals + last step's carry visible
+            float s_in = carry[par * kRsMaxCw + cw];  // state entering this super-step, then through the warps before mine
 #pragma unroll
             for (int w2 = 0; w2 < WPC - 1; ++w2)
                 if (w2 < ww) { const float2 t = wt[w2]; s_in = fmaf(t.x, s_in, t.y); }
@@ -1187,20 +1158,73 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
                 wp[i] = tv;
                 if (wbase == 0) wp[RL + i] = tv;  // keep the mirror of the ring head current
             }
-            if (ww == WPC - 1 && lane == 31) carry[(par ^ 1) * CW + cw] = sv;
-            if (tid == 0) {
-                if (ready != nullptr) need_input((k + 4) * (int64_t)S);
-                wait_free(k + 1);
-            }
-            comb_bar();                 // (B) ring writes of this super-step visible to every warp of the CTA; slot free
-            if (k + 1 < nsteps) stage_row(k + 1);  // the row the all-pass chain needs next; shipped after barrier (A)
+            if (ww == WPC - 1 && lane == 31) carry[(par ^ 1) * kRsMaxCw + cw] = sv;
+            ring_bar();                 // (B) ring writes of this super-step visible to the group and to the stagers
         }
-    } else if (home) {
+    } else if (is_stager) {
+        // ------------------------------------------------------------------ stager group (producer CTAs)
+        // Delayed outputs for the all-pass chain of super-step m: for every comb the S samples are one contiguous run of its
+        // ring (it continues into the mirror, never wraps), complete after barrier (B) of super-step m - 1 and not
+        // overwritten before super-step m + 1 has passed (the delays exceed S).  While the comb warps run super-step m the
+        // stagers add the combs' runs into a 16-byte aligned staging row and ONE lane hands the row to the bulk-copy engine,
+        // which writes the home CTA's dly row through distributed shared memory and completes the transaction on the
+        // home's full[slot] mbarrier -- no remote stores and no fences on the comb filters' critical path.  The staging row
+        // is reused for super-step m + depth, i.e. after free[slot] said that the all-pass group has consumed this one.
+        const int s = gq == 1 ? tid - 2 * 32 * WPC : tid - Cfg::kCombThreads;
+        int dl[kRsMaxCw];
+#pragma unroll
+        for (int j = 0; j < kRsMaxCw; ++j) dl[j] = g.comb_delay[c][comb0 + (j < ncomb ? j : 0)];
+        const uint32_t dly_home = map_to((uint32_t)__cvta_generic_to_shared(dly), home_rank) + (uint32_t)((gq - 1) * kRsDepth * kRevMaxS) * 4u;
+        const uint32_t full_home = map_to(bar0, home_rank);
+        auto ship_row = [&](int slot) {  // one lane, after the stagers' barrier that follows the staging writes + proxy fences
+            const float *srow = stage + slot * kRevMaxS;
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dly_home + (uint32_t)(slot * kRevMaxS) * 4u), "r"((uint32_t)__cvta_generic_to_shared(srow)),
+                           "r"((uint32_t)(S * 4)), "r"(full_home + 8u * slot) : "memory");
+        };
+        // row 0: nothing has been written to the rings yet -- all zeros
+        for (int i = s; i < S; i += nst) stage[i] = 0.0f;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        stager_bar();
+        if (s == 0) {
+            // streaming pair: acquire BEFORE the first row leaves -- the mixers take "row m has arrived" as proof that the
+            // input up to (m + 3) S is published (their dry loads have no flag polling of their own)
+            if (ready != nullptr) need_input(3 * (int64_t)S);
+            ship_row(0);
+        }
+        ring_bar();  // (B) of the prologue
+        int slot = 0, wb = 0;
+        uint32_t free_par = 1;  // the first wait (row kRsDepth) is for phase 0
+        for (int64_t k = 0; k < nsteps; ++k) {
+            if (s == 0 && ready != nullptr) need_input((k + 4) * (int64_t)S);  // what the comb warps prefetch after this barrier
+            ring_bar();  // (B) of super-step k: its ring writes are visible
+            if (++slot == kRsDepth) { slot = 0; free_par ^= 1u; }
+            wb = (wb == 2 * S) ? 0 : wb + S;
+            if (k + 1 >= nsteps) break;
+            // row k + 1 -> slot (k + 1) % depth, ring position ((k + 1) % 3) * S; the slot is free once the home's all-pass group
+            // has finished super-step k + 1 - depth (control only: the bulk copy out of the staging row is then long complete)
+            if (k + 1 >= kRsDepth) mbar_wait<kControl>(bar0 + 8u * (kRsDepth + slot), free_par);
+            float *srow = stage + slot * kRevMaxS;
+            for (int v4 = s; v4 < S / 4; v4 += nst) {
+                float4 acc;
+#pragma unroll
+                for (int cq = 0; cq < kRsMaxCw; ++cq) {
+                    if (cq < ncomb) {
+                        int rb = wb - dl[cq];
+                        if (rb < 0) rb += RL;
+                        const float *src = ring + cq * kCombRing + rb + 4 * v4;
+                        if (cq == 0) acc = make_float4(src[0], src[1], src[2], src[3]);
+                        else { acc.x = __fadd_rn(acc.x, src[0]); acc.y = __fadd_rn(acc.y, src[1]); acc.z = __fadd_rn(acc.z, src[2]); acc.w = __fadd_rn(acc.w, src[3]); }
+                    }
+                }
+                *reinterpret_cast<float4 *>(srow + 4 * v4) = acc;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my staging writes -> visible to the async proxy
+            stager_bar();
+            if (s == 0) ship_row(slot);
+        }
+    } else if (home && !comb_slot) {
         // ------------------------------------------------------------------ all-pass group of the home CTA (consumer)
-        // Per super-step: wait for the NSPLIT delayed rows, run the 4 all-passes over 5 sub-blocks, hand the wet row to
-        // the two MIXER groups (below) by bulk copy, free the slot.  Nothing else: the dry/wet mix with its global loads
-        // and stores, and the L <-> R wet exchange, took 60 % of this group's time when it did them itself
-        // (profiles/r02e_reverb_split.md, v10) and this group is the slowest stage of the pipeline.
         const int a = tid - Cfg::kCombThreads;
         int ad[4];
 #pragma unroll
@@ -1209,36 +1233,36 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
         const uint32_t mix_peer = map_to((uint32_t)__cvta_generic_to_shared(dly), peer_rank + 1);       // wet[.][1] of the other channel's
         const uint32_t mixfull_own = map_to(bar0 + 8u * (2 * kRsDepth + kRsWet), home_rank + 1);
         const uint32_t mixfull_peer = map_to(bar0 + 8u * (2 * kRsDepth + kRsWet), peer_rank + 1);
-        uint32_t free_of[NSPLIT];
+        uint32_t free_of[kRsProd];
 #pragma unroll
-        for (int gg = 0; gg < NSPLIT; ++gg) free_of[gg] = map_to(bar0 + 8u * kRsDepth, home_rank + gg);
+        for (int gg = 0; gg < kRsProd; ++gg) free_of[gg] = map_to(bar0 + 8u * kRsDepth, home_rank + 1 + gg);
         auto ap_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kRevSub) : "memory"); };
         int slot = 0, ws = 0;
-        uint32_t full_par = 0, wfree_par = 1;  // wfree: first wait (k = kRsWet) is for phase 0, so the parity starts at 1 ^ 1
+        uint32_t full_par = 0, wfree_par = 1;  // wfree: the first wait (k = kRsWet) is for phase 0
         int nbase = 0;
         for (int64_t k = 0; k < nsteps; ++k) {
             // the staging row of the wet samples is free once BOTH mixers have consumed super-step k - kRsWet (which also
             // means the two bulk copies out of it are complete); control only, and long since true in steady state
             if (k >= kRsWet && ws == 0) wfree_par ^= 1u;
             if (k >= kRsWet) mbar_wait<kControl>(bar0 + 8u * (2 * kRsDepth + ws), wfree_par);
-            mbar_wait<kTx>(bar0 + 8u * slot, full_par);  // the NSPLIT delayed rows of this super-step
+            mbar_wait<kTx>(bar0 + 8u * slot, full_par);  // the kRsProd delayed rows of this super-step
             const float *row = dly + slot * kRevMaxS;
             float *wown = wetb + ws * kRevMaxS;
             for (int sb = 0; sb < nsub; ++sb) {
                 const int off = sb * kRevSub + a;
                 if (off < S) {
                     const int n = nbase + off;
-                    // all 8 shared-memory loads up front: the four all-pass rings are distinct arrays and each stage reads
+                    // all 7 shared-memory loads up front: the four all-pass rings are distinct arrays and each stage reads
                     // >= 244 samples behind what this sub-block writes, but the compiler cannot know and would serialise every
                     // stage's load behind the previous stage's store (4 x ~30 cycles of latency on the critical chain)
-                    float cr[NSPLIT], bvv[4];
+                    float cr[kRsProd], bvv[4];
 #pragma unroll
-                    for (int j = 0; j < NSPLIT; ++j) cr[j] = row[j * kRsDepth * kRevMaxS + off];
+                    for (int j = 0; j < kRsProd; ++j) cr[j] = row[j * kRsDepth * kRevMaxS + off];
 #pragma unroll
                     for (int s2 = 0; s2 < 4; ++s2) bvv[s2] = ap[s2 * kApRing + ((n - ad[s2]) & (kApRing - 1))];
-                    float v = cr[0];  // sum of the 8 comb outputs: ((c0 + c1) + (c2 + c3)) + ... -- the producers pre-add their pair
+                    float v = cr[0];  // the producers pre-add their combs
 #pragma unroll
-                    for (int j = 1; j < NSPLIT; ++j) v = __fadd_rn(v, cr[j]);
+                    for (int j = 1; j < kRsProd; ++j) v = __fadd_rn(v, cr[j]);
 #pragma unroll
                     for (int s2 = 0; s2 < 4; ++s2) {
                         const float tv = undenorm(__fadd_rn(v, __fmul_rn(bvv[s2], 0.5f)));
@@ -1252,7 +1276,7 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
             }
             // Every all-pass thread has passed the barrier above: the wet row of this super-step is complete and dly[.][slot]
             // has been read.  ONE thread hands the wet row to the mixer of this channel (as its "own" row) and to the mixer of
-            // the other channel (as its "peer" row) and re-arms the slot; NSPLIT threads tell one producer CTA each that the
+            // the other channel (as its "peer" row) and re-arms the slot; kRsProd threads tell one producer CTA each that the
             // slot (and its staging row) is free.
             if (a == 0) {
                 const uint32_t src = (uint32_t)__cvta_generic_to_shared(wown);
@@ -1260,17 +1284,17 @@ __global__ void __launch_bounds__(RsCfg<NSPLIT, WPC>::kThreads, 1) reverb_split_
                              ::"r"(mix_own + (uint32_t)((ws * 2 + 0) * kRevMaxS) * 4u), "r"(src), "r"((uint32_t)(S * 4)), "r"(mixfull_own + 8u * ws) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(mix_peer + (uint32_t)((ws * 2 + 1) * kRevMaxS) * 4u), "r"(src), "r"((uint32_t)(S * 4)), "r"(mixfull_peer + 8u * ws) : "memory");
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"((uint32_t)(NSPLIT * S * 4)) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"((uint32_t)(kRsProd * S * 4)) : "memory");
             }
             __syncwarp();
             // relaxed: what has to be ordered -- every thread's READS of dly[.][slot] -- completed before the barrier above
-            if (a < NSPLIT)
+            if (a < kRsProd)
                 asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_of[a] + 8u * slot) : "memory");
             if (++slot == kRsDepth) { slot = 0; full_par ^= 1u; }
             if (++ws == kRsWet) ws = 0;
             nbase = (nbase + S) & (kApRing * 1024 - 1);
         }
-    } else if (gq == 1) {
+    } else if (gq == 1 && !comb_slot) {
         // ------------------------------------------------------------------ mixer group (CTA g == 1 of each channel)
         // y = wet_own * wet1 + wet_peer * wet2 + x * dry.  The two wet rows of a super-step arrive by bulk copy from the two
         // home CTAs (complete_tx on mixfull[ws]); the dry samples are re-read from global memory (L2 hits), prefetched one
@@ -1494,13 +1518,13 @@ cudaError_t launch_reverb(cudaStream_t st, SigView in, const float *in_peak, flo
             constexpr int kWpcA = 5, kWpcB = 4;  // 7 samples x 160 lanes = 1120; 8 x 128 = 1024
             static_assert(32 * kWpcA * 7 == 32 * kRevMaxSegF && 32 * kWpcB * 8 == 32 * 32, "super-step lengths");
             const bool big = seg == kRevMaxSegF;
-            KernS ks = big ? reverb_split_kernel<7, kWpcA, 4> : reverb_split_kernel<8, kWpcB, 4>;
-            const size_t ssm = big ? RsCfg<4, kWpcA>::kSmem : RsCfg<4, kWpcB>::kSmem;
+            KernS ks = big ? reverb_split_kernel<7, kWpcA> : reverb_split_kernel<8, kWpcB>;
+            const size_t ssm = big ? RsCfg<kWpcA>::kSmem : RsCfg<kWpcB>::kSmem;
             e = ensure_dyn_smem(reinterpret_cast<const void *>(ks), (int)ssm);
             if (e != cudaSuccess) return e;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(P * 8);
-            cfg.blockDim = dim3(big ? RsCfg<4, kWpcA>::kThreads : RsCfg<4, kWpcB>::kThreads);
+            cfg.blockDim = dim3(big ? RsCfg<kWpcA>::kThreads : RsCfg<kWpcB>::kThreads);
             cfg.dynamicSmemBytes = ssm;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];
