@@ -50,7 +50,7 @@ CONFIGS = {
             label="EQ+Compressor+2s-IR convolution reverb (mastering-conv)"),
 }
 ORACLE_KINDS = {"eq": ["eq"], "mastering-pb": ["eq", "comp", "reverb"], "basic": ["eq", "comp", "dist", "delay", "reverb"],
-                "mastering-conv": ["eq", "comp", "convreverb2s"]}
+                "mastering-conv": ["eq", "comp", "convreverb2s"], "mastering-dasp": ["eq", "lticomp", "convreverb2s"]}
 
 
 def resolve(args):

@@ -13,6 +13,7 @@ for p in 8 16 32 64 128 256 512 1024; do
 done
 timeout 900 python bench.py --config 4 --steps 1 --warmup 1 --iters 5 --cpu-sample 1 >> ${T}_bench_c4.jsonl 2>> ${T}_bench.err
 timeout 900 python bench.py --config 1 --steps 3 --warmup 1 --cpu-sample 2 >> ${T}_bench_c1.jsonl 2>> ${T}_bench.err
+timeout 900 python bench.py --chain mastering-dasp --steps 2 --warmup 1 --iters 10 --cpu-sample 2 >> ${T}_bench_dasp.jsonl 2>> ${T}_bench.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file ${T}_launches_p64.csv python scripts/dev_generation.py 64 1 > ${T}_ncu1.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file ${T}_launches_p8.csv python scripts/dev_generation.py 8 1 > ${T}_ncu2.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file ${T}_launches_c4.csv python scripts/dev_generation.py 16 1 30 mastering-conv > ${T}_ncu3.log 2>&1
@@ -22,9 +23,12 @@ timeout 600 ncu --set full --clock-control none --import-source on --profile-fro
 ncu -i ${T}_prof_dsp.ncu-rep --page raw --csv > ${T}_prof_dsp_raw.csv 2>/dev/null
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"crv_" -o ${T}_prof_crv -f python scripts/dev_generation.py 16 1 30 mastering-conv > ${T}_ncu6.log 2>&1
 ncu -i ${T}_prof_crv.ncu-rep --page raw --csv > ${T}_prof_crv_raw.csv 2>/dev/null
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"lti_" -o ${T}_prof_lti -f python scripts/dev_generation.py 16 1 10 mastering-dasp > ${T}_ncu8.log 2>&1
+ncu -i ${T}_prof_lti.ncu-rep --page raw --csv > ${T}_prof_lti_raw.csv 2>/dev/null
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file ${T}_launches_dasp.csv python scripts/dev_generation.py 16 1 10 mastering-dasp > ${T}_ncu9.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"reverb_split|compressor" -o ${T}_prof_p8 -f python scripts/dev_generation.py 8 1 > ${T}_ncu7.log 2>&1
 ncu -i ${T}_prof_p8.ncu-rep --page raw --csv > ${T}_prof_p8_raw.csv 2>/dev/null
-rm -f ${T}_prof_conv.ncu-rep ${T}_prof_dsp.ncu-rep ${T}_prof_crv.ncu-rep ${T}_prof_p8.ncu-rep
+rm -f ${T}_prof_conv.ncu-rep ${T}_prof_dsp.ncu-rep ${T}_prof_crv.ncu-rep ${T}_prof_p8.ncu-rep ${T}_prof_lti.ncu-rep
 grep -E "passed|failed|FAILED|rc=" ${T}_gpu_tests.log | tail -5; tail -2 ${T}_smoke.log; tail -3 ${T}_bench.err
 python - <<'PY'
 import json,glob
