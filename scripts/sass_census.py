@@ -4,7 +4,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "st_ito_b200", "libstito.so")
 sass = subprocess.check_output(["cuobjdump", "-sass", lib], text=True)
-ops = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMAPF", "SYNCS", "UCGABAR", "ST.E", "LD.E", "LDS", "STS", "DFMA", "DMUL", "DADD",
+ops = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMAPF", "UBLKCP", "SYNCS", "UCGABAR", "ST.E", "LD.E", "LDS", "STS", "DFMA", "DMUL", "DADD",
        "FFMA", "MUFU", "SHFL", "BAR", "ATOM", "RED", "MAPA", "LDG", "STG", "HMMA", "NANOSLEEP"]
 counts, name = collections.OrderedDict(), None
 for line in sass.splitlines():
@@ -22,7 +22,7 @@ for line in sass.splitlines():
             if op == o or op.startswith(o + ".") or (o in ("ST.E", "LD.E") and op.startswith(o)):
                 counts[name][o] += 1
 print("# SASS opcode census of st_ito_b200/libstito.so (cuobjdump -sass, sm_100a). UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, "
-      "LDTM = tcgen05.ld, UTMALDG = TMA tensor load, SYNCS = mbarrier ops, UCGABAR = cluster barrier, MAPA = DSMEM address map")
+      "LDTM = tcgen05.ld, UTMALDG = TMA tensor load, UBLKCP = cp.async.bulk (shared -> DSMEM), SYNCS = mbarrier ops, UCGABAR = cluster barrier, MAPA = DSMEM address map")
 print("kernel,instructions," + ",".join(ops))
 for k, c in counts.items():
     print(f"\"{k}\",{c['_total']}," + ",".join(str(c[o]) for o in ops))
