@@ -455,6 +455,9 @@ int run_chain(stito_handle *h, cudaStream_t st, SigView in, int chs, int64_t L, 
             }
             case STITO_FX_COMPRESSOR: {
                 int *ready = nullptr;
+                // (Tried for 15..18 candidates, where the cluster-split Freeverb fits the GPU alone but not next to the
+                // compressor's CTAs: compressor THEN split reverb.  Slower -- 16 clusters of 8 do not all become resident at
+                // once (a cluster must sit inside one GPC), the last one runs as a second wave: DSP 1.59 vs 1.32 ms.)
                 const bool pair = streaming_on && !c.normalize_stages && f + 1 < c.num_fx && cur_chs == 2 &&
                                   c.fx[f + 1].kind == STITO_FX_REVERB && c.fx[f + 1].num_channels == 2 &&
                                   reverb_can_stream(h->rgeom) && 2 * P * cur_chs + 16 <= sm_count;
