@@ -83,3 +83,39 @@ def test_plugin_wrappers_agree_on_the_parameter_schema():
         assert (a.parameters[k].min_value, a.parameters[k].max_value) == (b.parameters[k].min_value, b.parameters[k].max_value)
         assert a.parameters[k].raw_value == pytest.approx(b.parameters[k].raw_value)
     assert effects.is_native_plugin(a) and list(effects.make_chain("mastering-dasp")) == ["ParametricEQ", "LTICompressor", "NoiseShapedReverb"]
+
+
+@pytest.mark.parametrize("L,attack_ms", [(3000, 250.0), (4096, 37.0), (4097, 250.0), (20000, 0.1), (50001, 120.0)])
+def test_chunked_fold_and_apply_equal_the_frequency_sampled_filter(L, attack_ms):
+    """The decomposition lticomp.cu uses, restated in numpy: 4096-sample chunks folded into affine maps s -> A s + B
+    (A = alpha^valid), entering states from sum_j B_j * prod_{i>j} A_i with alpha^(4096 * count) for the full chunks in
+    between, the wrap-around term alpha^n0 * y0[L-1] * wrap, then the recurrence inside every chunk."""
+    from oracle import lticomp as lc
+
+    CH = 4096
+    g = -12.0 * np.abs(np.random.RandomState(L).randn(L)).astype(np.float32)
+    alpha = lc.attack_alpha(attack_ms, SR)
+    a, b0, ln_a = float(alpha), float(np.float32(1.0) - alpha), np.log(float(alpha))
+    nchunks = (L + CH - 1) // CH
+    n_fft = lc.fsm_fft_size(L)
+    wrap = np.exp(ln_a * (n_fft - L)) / (-np.expm1(ln_a * n_fft))
+
+    def run(seg, s):  # the recurrence over one chunk from state s; returns the states
+        out = np.empty(len(seg))
+        for i, v in enumerate(seg.astype(np.float64)):
+            s = a * s + b0 * v
+            out[i] = s
+        return out
+
+    maps = []
+    for c in range(nchunks):
+        seg = g[c * CH:(c + 1) * CH]
+        maps.append((a ** len(seg), run(seg, 0.0)[-1]))
+    last_a = maps[-1][0]
+    y_end = sum(maps[j][1] * np.exp(ln_a * (nchunks - 2 - j) * CH) * last_a for j in range(nchunks - 1)) + maps[-1][1]
+    y_init = y_end * wrap
+    got = np.empty(L)
+    for c in range(nchunks):
+        s_in = sum(maps[j][1] * np.exp(ln_a * (c - 1 - j) * CH) for j in range(c)) + y_init * np.exp(ln_a * c * CH)
+        got[c * CH:(c + 1) * CH] = run(g[c * CH:(c + 1) * CH], s_in)
+    np.testing.assert_allclose(got, lc.smooth_gain_fsm(g, alpha), rtol=0, atol=1e-9)
