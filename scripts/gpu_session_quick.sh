@@ -7,7 +7,7 @@ for p in 8 16; do
   timeout 600 python bench.py --pop $p --steps 2 --warmup 1 --iters 10 --no-cpu-baseline >> ${T}_pop.jsonl 2>> ${T}_bench.err
 done
 timeout 600 python bench.py --steps 3 --warmup 1 --cpu-sample 2 > ${T}_bench.jsonl 2>> ${T}_bench.err
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file ${T}_launches_p8.csv python scripts/dev_generation.py 8 1 > ${T}_ncu.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file ${T}_launches_p8.csv python scripts/dev_generation.py ${2:-8} 1 > ${T}_ncu.log 2>&1
 tail -3 ${T}_tests.log; tail -3 ${T}_bench.err
 python - "$T" <<'PY'
 import json,glob,sys
