@@ -125,6 +125,29 @@ def test_load_plugins_and_compile_chain_index_bookkeeping(capsys):
         load_plugins({"x": {"num_channels": 1}})
 
 
+def test_compile_chain_of_the_dasp_style_effects(capsys):
+    """SURVEY row R2 as ES-path plugins: make_chain("mastering-dasp") -> chain kinds 0 / 6 / 5 with their integer options."""
+    from st_ito_b200 import _lib, effects
+    from st_ito_b200.engine import compile_chain
+    from st_ito_b200.style_transfer import load_plugins
+
+    plugins, D, init = load_plugins(effects.make_chain("mastering-dasp"))
+    capsys.readouterr()
+    assert D == (1 + 18) + (1 + 6) + (1 + 25) == len(init)
+    desc, Dc = compile_chain(plugins, 48000)
+    assert Dc == D and desc.num_fx == 3
+    eq, comp, rev = desc.fx[0], desc.fx[1], desc.fx[2]
+    assert (eq.kind, comp.kind, rev.kind) == (_lib.FX_EQ, _lib.FX_LTI_COMPRESSOR, _lib.FX_CONV_REVERB)
+    assert comp.num_params == 6 and comp.num_channels == 2 and list(comp.w_index[:6]) == list(range(20, 26))
+    assert list(comp.iopt) == [512, 0, 0, 0]          # lookahead_samples of effects.py:646
+    assert rev.num_params == 25 and list(rev.iopt)[:2] == [96000, 0]  # 2 s impulse response, noise seed
+    # the plugin's ranges are the reference's (effects.py:629-634): changing one makes it a foreign plugin
+    inst = effects.BasicLTICompressor(lookahead_samples=0)
+    assert effects.is_native_plugin(inst) and inst.stito_iopt == (0, 0, 0, 0)
+    inst.parameters["knee_db"].max_value = 12.0
+    assert not effects.is_native_plugin(inst)
+
+
 def test_run_optim_style_loader_has_no_bypass_slots():
     """scripts/run_optim.py:410-437 records parameter_names without our_bypass: D = 18 for the EQ."""
     from st_ito_b200.engine import compile_chain
