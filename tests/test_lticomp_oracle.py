@@ -119,3 +119,56 @@ def test_chunked_fold_and_apply_equal_the_frequency_sampled_filter(L, attack_ms)
         s_in = sum(maps[j][1] * np.exp(ln_a * (c - 1 - j) * CH) for j in range(c)) + y_init * np.exp(ln_a * c * CH)
         got[c * CH:(c + 1) * CH] = run(g[c * CH:(c + 1) * CH], s_in)
     np.testing.assert_allclose(got, lc.smooth_gain_fsm(g, alpha), rtol=0, atol=1e-9)
+
+
+def test_float32_torch_restatement_of_the_upstream_function_agrees():
+    """dasp_pytorch.compressor as recalled, written the way upstream writes it (torch float32 end to end, including the
+    float32 rfft / irfft of lfilter_via_fsm), next to the oracle (float32 gain computer, float64 smoothing): the two differ
+    only by the float32 FFT's rounding -- this bounds how far a float32 torch run of the real thing can sit from the
+    oracle, i.e. what "parity unpinned" costs numerically for this effect (measured here: 1e-7 ... 2e-5 of the peak)."""
+    import torch
+
+    from oracle import lticomp as lc
+
+    def upstream(x, sample_rate, threshold_db, ratio, attack_ms, release_ms, knee_db, makeup_gain_db, eps=1e-8,
+                 lookahead_samples=0):
+        bs, chs, seq_len = x.size()
+        x_side = x.sum(dim=1, keepdim=True).view(-1, 1, seq_len)
+        threshold_db, ratio, attack_ms = threshold_db.view(-1, 1, 1), ratio.view(-1, 1, 1), attack_ms.view(-1, 1, 1)
+        knee_db, makeup_gain_db = knee_db.view(-1, 1, 1), makeup_gain_db.view(-1, 1, 1)
+        normalized_attack_time = sample_rate * (attack_ms / 1e3)
+        constant = torch.tensor([9.0]).type_as(attack_ms)
+        alpha_A = torch.exp(-torch.log(constant) / normalized_attack_time)
+        x_db = 20 * torch.log10(torch.abs(x_side).clamp(eps))
+        x_sc = x_db.clone()
+        idx = torch.logical_and(x_db >= (threshold_db - (knee_db / 2)), x_db <= (threshold_db + (knee_db / 2)))
+        x_sc_below = x_db + ((1 / ratio) - 1) * ((x_db - threshold_db + (knee_db / 2)) ** 2) / (2 * knee_db)
+        x_sc[idx] = x_sc_below[idx]
+        idx = x_db > (threshold_db + (knee_db / 2))
+        x_sc_above = threshold_db + ((x_db - threshold_db) / ratio)
+        x_sc[idx] = x_sc_above[idx]
+        g_c = x_sc - x_db
+        b = torch.cat([(1 - alpha_A), torch.zeros(bs, 1, 1)], dim=-1).squeeze(1)
+        a = torch.cat([torch.ones(bs, 1, 1), -alpha_A], dim=-1).squeeze(1)
+        n_fft = int(2 ** torch.ceil(torch.log2(torch.tensor(g_c.shape[-1] + g_c.shape[-1] - 1))))
+        H = (torch.fft.rfft(b, n_fft) / torch.fft.rfft(a, n_fft)).unsqueeze(1)
+        g_c_attack = torch.fft.irfft(torch.fft.rfft(g_c, n_fft) * H, n_fft)[..., :seq_len]
+        if lookahead_samples > 0:
+            x = torch.roll(x, lookahead_samples, dims=-1)
+            x[:, :, :lookahead_samples] = 0
+        return x * 10 ** ((g_c_attack + makeup_gain_db) / 20.0)
+
+    rng = np.random.RandomState(5)
+    for L, chs in ((20000, 2), (48000, 1)):
+        x = test_signal(chs, L, seed=L)
+        x = (0.7 * x / np.abs(x).max()).astype(np.float32)
+        for _ in range(4):
+            thr, ratio, att = -60 * rng.rand(), 1 + 19 * rng.rand(), 0.1 + 249.9 * rng.rand()
+            knee, mk = 1 + 23 * rng.rand(), 24 * rng.rand()
+            t = lambda v: torch.tensor([v], dtype=torch.float32)
+            want = upstream(torch.from_numpy(x[None].copy()), SR, t(thr), t(ratio), t(att), t(100.0), t(knee), t(mk),
+                            lookahead_samples=512)[0].numpy()
+            got = lc.lti_compressor(x, SR, np.float32(thr), np.float32(ratio), np.float32(att), 100.0, np.float32(knee),
+                                    np.float32(mk), 512)
+            peak = np.abs(want).max()
+            assert np.abs(got - want).max() <= 5e-5 * peak, (L, chs, thr, ratio, att, np.abs(got - want).max() / peak)
