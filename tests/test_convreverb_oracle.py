@@ -58,3 +58,37 @@ def test_oracle_reverb_properties():
     assert np.abs(out[:, 4096:]).max() < 1e-6
     with pytest.raises(AssertionError):
         ref.parameters["mix"].set_value(1.5)
+
+
+def test_float32_torch_restatement_of_the_upstream_function_agrees():
+    """dasp_pytorch.noise_shaped_reverberation as recalled, written the way upstream writes it (torch float32: grouped
+    conv1d of the noise with the filter bank, envelope, mean over bands, direct conv1d with the flipped impulse response),
+    fed the SAME white noise as the oracle, next to the oracle (float64 FFT convolutions): bounds what "parity unpinned"
+    costs numerically for this effect when the noise is given."""
+    import torch
+
+    from oracle import convreverb as cr
+
+    sr, num_samples, taps, L = 48000.0, 6000, cr.NUM_TAPS, 9000
+    rng = np.random.RandomState(11)
+    x = test_signal(2, L, seed=3)
+    x = (x / np.abs(x).max()).astype(np.float32)
+    span = num_samples + taps - 1
+    wn = torch.from_numpy(cr.white_noise(21, 2 * cr.NUM_BANDS * span).reshape(2, cr.NUM_BANDS, span).copy())
+    filters = torch.from_numpy(cr.octave_band_filterbank(taps, sr)).unsqueeze(1)           # [12, 1, taps]
+    bands = cr.filtered_noise_bands(sr, num_samples, 21)
+    for _ in range(3):
+        gains, decays, mix = rng.rand(12).astype(np.float32), rng.rand(12).astype(np.float32), np.float32(rng.rand())
+        xt = torch.from_numpy(x[None].copy())                                              # [1, 2, L]
+        wn_filt = torch.nn.functional.conv1d(wn, filters, groups=cr.NUM_BANDS).view(1, 2, cr.NUM_BANDS, num_samples)
+        t = torch.linspace(0, 1, steps=num_samples)
+        band_decays = torch.from_numpy(decays).view(1, 1, -1, 1) * 10.0 + 1.0
+        env = torch.exp(-band_decays * t.view(1, 1, 1, -1))
+        wn_filt = wn_filt * (env * torch.from_numpy(gains).view(1, 1, -1, 1))
+        ir = wn_filt.mean(2, keepdim=True)[0]                                              # [2, 1, num_samples]
+        x_pad = torch.nn.functional.pad(xt, (num_samples - 1, 0))
+        y = torch.nn.functional.conv1d(x_pad, torch.flip(ir, dims=[-1]), groups=2)
+        want = ((1 - float(mix)) * xt + float(mix) * y)[0].numpy()
+        got = cr.noise_shaped_reverberation(x, sr, gains, decays, mix, bands)
+        peak = np.abs(want).max()
+        assert np.abs(got - want).max() <= 2e-5 * peak, np.abs(got - want).max() / peak
